@@ -1,0 +1,343 @@
+// tcgen05 GEMM for sm_100a:  C[M,N] = epilogue(A[M,K] . W[N,K]^T), fp32 accumulation in TMEM.
+//
+//   - operands K-major in global memory, tiles of 128 bytes along K (64 bf16 / 32 tf32)
+//     staged by TMA (SWIZZLE_128B) into a multi-stage shared-memory ring;
+//   - one elected thread issues tcgen05.mma (M=128, N=BN, K=16|8 per instruction), the
+//     accumulator tile lives in TMEM (BN fp32 columns x 128 lanes);
+//   - four epilogue warps read TMEM with tcgen05.ld (32 lanes x 32 columns each) and apply
+//     bias / residual / SiLU / SwiGLU before writing fp32 and/or bf16 rows;
+//   - Conv1d is the same kernel: the K loop walks (tap, channel-block) and shifts the A row
+//     coordinate by `tap`, so no im2col buffer exists anywhere.
+//
+// Replaces, for the hot path: torch addmm/mm behind transformers modeling_qwen2.py:46-48
+// (MLP), :217-219 (q/k/v), :244 (o_proj), :475 (lm_head) and the codec's Linear / Conv1d
+// layers.
+#include "common.cuh"
+#include "internal.h"
+
+namespace nt {
+
+struct GemmEpilogue {
+  const float* bias;
+  const float* residual;
+  long long ldr;
+  int act;  // nt_act
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  long long ldc;
+  int valid_period, valid_len;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int A_BYTES = BM * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN <= 64) ? 8 : (BN == 128 ? 6 : 4);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int kFmt, int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep, int M,
+               int N, int num_kb, int kb_per_tap) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int BK_ELEMS = (kFmt == 2) ? 32 : 64;  // 128 bytes along K
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t pad = (1024u - (raw_addr & 1023u)) & 1023u;
+  uint8_t* tiles = smem_raw + pad;  // 1024-byte aligned (SWIZZLE_128B atoms)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* acc_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = warp_id();
+  const int lane = lane_id();
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * Cfg::BM;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(acc_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  pdl_wait();  // inputs (A, residual) may come from the previous kernel in the stream
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        uint8_t* sa = tiles + s * Cfg::STAGE_BYTES;
+        uint8_t* sb = sa + Cfg::A_BYTES;
+        const int tap = kb / kb_per_tap;
+        const int acol = (kb - tap * kb_per_tap) * BK_ELEMS;
+        tma_load_2d(sa, &tmA, acol, m0 + tap, &full_bar[s]);
+        tma_load_2d(sb, &tmB, kb * BK_ELEMS, n0, &full_bar[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(kFmt, 128, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+        const uint32_t sb = sa + Cfg::A_BYTES;
+        const uint64_t adesc = umma_desc_sw128(sa);
+        const uint64_t bdesc = umma_desc_sw128(sb);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per stage
+          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+          if (kFmt == 2)
+            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+          else
+            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+      }
+      umma_commit(acc_bar);  // accumulator complete
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int q = warp - 4;  // TMEM lane quarter (== warp % 4)
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    const int row = m0 + q * 32 + lane;
+    bool row_ok = row < M;
+    if (ep.valid_period > 0 && (row % ep.valid_period) >= ep.valid_len) row_ok = false;
+    const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t raw[32];
+      tmem_ld32(trow + c * 32, raw);
+      tmem_ld_wait();
+      const int col0 = n0 + c * 32;
+      if (!row_ok || col0 >= N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      const bool full = (col0 + 32 <= N);
+      if (ep.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || col0 + j < N) v[j] += __ldg(ep.bias + col0 + j);
+      }
+      if (ep.act == NT_ACT_SWIGLU) {
+        // (gate, up) interleaved on the N axis -> 16 outputs
+        const long long ocol0 = col0 >> 1;
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = silu(v[2 * j]) * v[2 * j + 1];
+        const int nvalid = full ? 16 : ((N - col0) >> 1);
+        if (ep.out_bf16) {
+          __nv_bfloat16* dst = ep.out_bf16 + row * ep.ldc + ocol0;
+          if (nvalid == 16 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+            uint4 p0 = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]),
+                                  pack_bf16x2(o[6], o[7]));
+            uint4 p1 = make_uint4(pack_bf16x2(o[8], o[9]), pack_bf16x2(o[10], o[11]), pack_bf16x2(o[12], o[13]),
+                                  pack_bf16x2(o[14], o[15]));
+            reinterpret_cast<uint4*>(dst)[0] = p0;
+            reinterpret_cast<uint4*>(dst)[1] = p1;
+          } else {
+            for (int j = 0; j < nvalid; ++j) dst[j] = __float2bfloat16(o[j]);
+          }
+        }
+        if (ep.out_f32) {
+          float* dst = ep.out_f32 + row * ep.ldc + ocol0;
+          for (int j = 0; j < nvalid; ++j) dst[j] = o[j];
+        }
+        continue;
+      }
+      if (ep.residual) {
+        const float* r = ep.residual + row * ep.ldr + col0;
+        if (full && ((reinterpret_cast<uintptr_t>(r) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = reinterpret_cast<const float4*>(r)[j];
+            v[4 * j] += t.x, v[4 * j + 1] += t.y, v[4 * j + 2] += t.z, v[4 * j + 3] += t.w;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) v[j] += r[j];
+        }
+      }
+      if (ep.act == NT_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+      }
+      if (ep.out_f32) {
+        float* dst = ep.out_f32 + row * ep.ldc + col0;
+        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) dst[j] = v[j];
+        }
+      }
+      if (ep.out_bf16) {
+        __nv_bfloat16* dst = ep.out_bf16 + row * ep.ldc + col0;
+        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            reinterpret_cast<uint4*>(dst)[j] =
+                make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) dst[j] = __float2bfloat16(v[j]);
+        }
+      }
+    }
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, BN);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// rows x cols (elements) matrix with row stride ld (elements); box = box_rows x 128 bytes.
+static int make_tmap(CUtensorMap* out, nt_dtype dt, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint32_t box_rows) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (!fn) return set_error(NT_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  const uint32_t esz = (dt == NT_BF16) ? 2 : 4;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * esz};
+  cuuint32_t box[2] = {128 / esz, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, dt == NT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(NT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(r));
+  return NT_OK;
+}
+
+template <int kFmt, int BN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int num_kb,
+                       int kb_per_tap, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  auto kern = gemm_tc_kernel<kFmt, BN>;
+  if (!attr_set) {
+    NT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + Cfg::BM - 1) / Cfg::BM, 1);
+  return launch_kernel(kern, grid, dim3(256), Cfg::SMEM_BYTES, stream, /*pdl=*/true, ta, tb, ep, M, N, num_kb,
+                       kb_per_tap);
+}
+
+int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error(NT_ERR_INVALID, "gemm: empty problem");
+  const int esz = a.dtype == NT_BF16 ? 2 : 4;
+  const int bk = 128 / esz;
+  if ((a.lda * esz) % 16 || (a.ldw * esz) % 16) return set_error(NT_ERR_INVALID, "gemm: row strides must be 16-byte multiples");
+  if ((reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.W)) & 15)
+    return set_error(NT_ERR_INVALID, "gemm: operands must be 16-byte aligned");
+  if (a.act == NT_ACT_SWIGLU && (a.N & 1)) return set_error(NT_ERR_INVALID, "gemm: SwiGLU needs even N");
+  if (a.act == NT_ACT_SWIGLU && a.residual) return set_error(NT_ERR_INVALID, "gemm: SwiGLU + residual unsupported");
+  if (!a.out_f32 && !a.out_bf16) return set_error(NT_ERR_INVALID, "gemm: no output");
+
+  // Conv1d-as-GEMM: A rows overlap (lda < K) -> K loop walks taps, shifting the A row.
+  int taps = 1;
+  uint64_t a_cols = a.K;
+  if (a.lda < a.K) {
+    if (a.K % a.lda || a.lda % bk) return set_error(NT_ERR_INVALID, "gemm: overlapped A needs K %% lda == 0 and lda %% %d == 0", bk);
+    taps = int(a.K / a.lda);
+    a_cols = a.lda;
+  }
+  const int num_kb = (a.K + bk - 1) / bk;
+  const int kb_per_tap = (taps > 1) ? int(a.lda / bk) : num_kb;
+  // rows reachable through the tap shift must stay addressable: caller guarantees
+  // A has M + taps - 1 rows.
+  const uint64_t a_rows = uint64_t(a.M) + taps - 1;
+
+  // tile-N choice: keep >= ~1 wave of CTAs when the problem allows it
+  const int mt = (a.M + 127) / 128;
+  int bn = 128;
+  if (mt * ((a.N + 127) / 128) < 120) bn = 64;
+  if (mt * ((a.N + 63) / 64) < 100) bn = 32;
+  if (a.act == NT_ACT_SWIGLU && bn < 64) bn = 64;
+
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, a.dtype, a.A, a_rows, a_cols, a.lda, 128);
+  if (rc) return rc;
+  rc = make_tmap(&tb, a.dtype, a.W, a.N, a.K, a.ldw, bn);
+  if (rc) return rc;
+
+  GemmEpilogue ep;
+  ep.bias = a.bias;
+  ep.residual = a.residual;
+  ep.ldr = a.ldr;
+  ep.act = a.act;
+  ep.out_f32 = a.out_f32;
+  ep.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a.out_bf16);
+  ep.ldc = a.ldc;
+  ep.valid_period = a.valid_period;
+  ep.valid_len = a.valid_len;
+
+#define NT_GEMM_CASE(FMT, BNV) return launch_gemm<FMT, BNV>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)
+  if (a.dtype == NT_BF16) {
+    if (bn == 128) NT_GEMM_CASE(1, 128);
+    if (bn == 64) NT_GEMM_CASE(1, 64);
+    NT_GEMM_CASE(1, 32);
+  } else {
+    if (bn == 128) NT_GEMM_CASE(2, 128);
+    if (bn == 64) NT_GEMM_CASE(2, 64);
+    NT_GEMM_CASE(2, 32);
+  }
+#undef NT_GEMM_CASE
+}
+
+}  // namespace nt
+
+extern "C" int nt_gemm(const nt_gemm_args* args, void* stream) {
+  if (!args) return nt::set_error(NT_ERR_INVALID, "nt_gemm: null args");
+  return nt::gemm_dispatch(*args, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,61 @@
+// Host-side internals shared by the translation units of libneutts_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <utility>
+
+#include "../../include/neutts_b200.h"
+
+namespace nt {
+
+int set_error(int code, const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define NT_CUDA_CHECK(expr)                                                                          \
+  do {                                                                                               \
+    cudaError_t _e = (expr);                                                                         \
+    if (_e != cudaSuccess)                                                                           \
+      return ::nt::set_error(NT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// Launch with optional programmatic-dependent-launch attribute (the kernel must call
+// pdl_wait() before touching anything a predecessor writes).
+template <typename... KArgs, typename... Args>
+int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                  Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+  if (e != cudaSuccess) return set_error(NT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return NT_OK;
+}
+
+int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream);
+
+// workspace carving helper (256-byte aligned sub-allocations from a caller-owned buffer)
+struct Arena {
+  uint8_t* base;
+  size_t size, off;
+  Arena(void* p, size_t n) : base(static_cast<uint8_t*>(p)), size(n), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = (count * sizeof(T) + 255) & ~size_t(255);
+    T* r = reinterpret_cast<T*>(base ? base + off : nullptr);
+    off += bytes;
+    return r;
+  }
+  bool ok() const { return off <= size; }
+};
+
+}  // namespace nt

@@ -1,0 +1,461 @@
+// C-ABI orchestration of the speech-LM path: prefill (tensor-core GEMMs), decode steps
+// (PDL-chained streaming kernels replayed from a CUDA graph), fused sampler.
+// Replaces the loop at transformers generation/utils.py:2743-2805 as reached from
+// neutts/neutts.py:338-347; nothing here synchronises with the host between steps
+// (the reference syncs every step at utils.py:2805).
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "lm_kernels.cuh"
+
+namespace nt {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static bool env_flag(const char* name) {
+  const char* v = getenv(name);
+  return v && v[0] && v[0] != '0';
+}
+
+}  // namespace nt
+
+using namespace nt;
+
+struct nt_lm {
+  nt_lm_config cfg;
+  int qkv_n, num_sms, max_splits, nchunks, max_rows;
+  const __nv_bfloat16* embed;
+  const __nv_bfloat16* lm_head;
+  const float* final_norm;
+  std::vector<const float*> ln1, bqkv, ln2;
+  std::vector<const __nv_bfloat16*> wqkv, wo, wgu, wd;
+  // workspace
+  float *h, *q, *attn, *act, *logits, *part_o, *part_ml, *cand_val, *inv_freq, *qkv, *h_last;
+  int *counters, *cand_idx, *tok_seq, *tok_pos, *cu_dev, *last_rows, *iota;
+  __nv_bfloat16 *xn, *attn_bf16, *act_bf16;
+  // cached decode-step graph
+  cudaGraphExec_t graph = nullptr;
+  std::vector<uint8_t> graph_key;
+  bool prefilled = false;
+};
+
+template <typename F>
+static size_t lm_carve(const nt_lm_config& c, void* ws, size_t bytes, F&& assign) {
+  Arena a(ws, bytes);
+  const int H = c.hidden, I = c.inter, V = c.vocab_size;
+  const int qkv_n = (c.n_heads + 2 * c.n_kv_heads) * 64;
+  const int rows = c.max_prefill_tokens > c.max_batch ? c.max_prefill_tokens : c.max_batch;
+  const int max_splits = c.max_ctx / c.page_size;
+  assign(a, H, I, V, qkv_n, rows, max_splits);
+  return a.off;
+}
+
+#define LM_CARVE_BODY(L)                                                                       \
+  [&](Arena& a, int H, int I, int V, int qkv_n, int rows, int max_splits) {                    \
+    (L)->h = a.take<float>(size_t(rows) * H);                                                  \
+    (L)->q = a.take<float>(size_t(rows) * c.n_heads * 64);                                     \
+    (L)->attn = a.take<float>(size_t(c.max_batch) * c.n_heads * 64);                           \
+    (L)->act = a.take<float>(size_t(c.max_batch) * I);                                         \
+    (L)->logits = a.take<float>(size_t(c.max_batch) * V);                                      \
+    (L)->part_o = a.take<float>(size_t(c.max_batch) * c.n_heads * max_splits * 64);            \
+    (L)->part_ml = a.take<float>(size_t(c.max_batch) * c.n_heads * max_splits * 2);            \
+    (L)->cand_val = a.take<float>(sampler_scratch_floats(c.max_batch, V));                     \
+    (L)->cand_idx = a.take<int>(sampler_scratch_floats(c.max_batch, V));                       \
+    (L)->inv_freq = a.take<float>(64);                                                         \
+    (L)->qkv = a.take<float>(size_t(rows) * qkv_n);                                            \
+    (L)->h_last = a.take<float>(size_t(c.max_batch) * H);                                      \
+    (L)->counters = a.take<int>(size_t(c.max_batch) * c.n_kv_heads);                           \
+    (L)->tok_seq = a.take<int>(rows);                                                          \
+    (L)->tok_pos = a.take<int>(rows);                                                          \
+    (L)->cu_dev = a.take<int>(c.max_batch + 1);                                                \
+    (L)->last_rows = a.take<int>(c.max_batch);                                                 \
+    (L)->iota = a.take<int>(c.max_batch);                                                      \
+    (L)->xn = a.take<__nv_bfloat16>(size_t(rows) * H);                                         \
+    (L)->attn_bf16 = a.take<__nv_bfloat16>(size_t(rows) * c.n_heads * 64);                     \
+    (L)->act_bf16 = a.take<__nv_bfloat16>(size_t(rows) * I);                                   \
+  }
+
+static int lm_check_config(const nt_lm_config* c) {
+  if (!c) return set_error(NT_ERR_INVALID, "null config");
+  if (c->head_dim != 64) return set_error(NT_ERR_INVALID, "head_dim %d unsupported (64 only)", c->head_dim);
+  if (c->page_size != 64) return set_error(NT_ERR_INVALID, "page_size %d unsupported (64 only)", c->page_size);
+  if (c->hidden % 64 || c->inter % 64) return set_error(NT_ERR_INVALID, "hidden/inter must be multiples of 64");
+  if (c->n_heads % c->n_kv_heads || c->n_heads / c->n_kv_heads > 8)
+    return set_error(NT_ERR_INVALID, "unsupported GQA ratio %d/%d", c->n_heads, c->n_kv_heads);
+  if (c->vocab_size & 1) return set_error(NT_ERR_INVALID, "vocab_size must be even");
+  if (c->max_ctx % 64 || c->max_ctx <= 0) return set_error(NT_ERR_INVALID, "max_ctx must be a positive multiple of 64");
+  if (c->max_batch < 1 || c->max_prefill_tokens < 1 || c->num_pages < 1) return set_error(NT_ERR_INVALID, "bad sizes");
+  return NT_OK;
+}
+
+extern "C" const char* nt_last_error(void) { return g_err; }
+extern "C" int nt_abi_version(void) { return 1; }
+extern "C" uint64_t nt_launch_count(void) { return g_launches.load(); }
+
+extern "C" size_t nt_lm_workspace_bytes(const nt_lm_config* cfg) {
+  if (lm_check_config(cfg)) return 0;
+  const nt_lm_config& c = *cfg;
+  nt_lm dummy;
+  return lm_carve(c, nullptr, 0, LM_CARVE_BODY(&dummy)) + 256;
+}
+
+extern "C" int nt_lm_create(const nt_lm_config* cfg, const nt_lm_weights* w, void* workspace, size_t workspace_bytes,
+                            nt_lm** out) {
+  int rc = lm_check_config(cfg);
+  if (rc) return rc;
+  if (!w || !workspace || !out) return set_error(NT_ERR_INVALID, "nt_lm_create: null argument");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return set_error(NT_ERR_INVALID, "workspace must be 256-byte aligned");
+  const nt_lm_config& c = *cfg;
+  nt_lm* lm = new nt_lm();
+  lm->cfg = c;
+  const size_t need = lm_carve(c, workspace, workspace_bytes, LM_CARVE_BODY(lm));
+  if (need > workspace_bytes) {
+    delete lm;
+    return set_error(NT_ERR_NOMEM, "workspace too small: need %zu, got %zu", need, workspace_bytes);
+  }
+  lm->qkv_n = (c.n_heads + 2 * c.n_kv_heads) * 64;
+  lm->max_splits = c.max_ctx / c.page_size;
+  lm->nchunks = sampler_nchunks(c.vocab_size);
+  lm->max_rows = c.max_prefill_tokens > c.max_batch ? c.max_prefill_tokens : c.max_batch;
+  lm->embed = static_cast<const __nv_bfloat16*>(w->embed);
+  lm->lm_head = static_cast<const __nv_bfloat16*>(w->lm_head);
+  lm->final_norm = w->final_norm;
+  for (int l = 0; l < c.n_layers; ++l) {
+    lm->ln1.push_back(w->ln1[l]);
+    lm->bqkv.push_back(w->bqkv[l]);
+    lm->ln2.push_back(w->ln2[l]);
+    lm->wqkv.push_back(static_cast<const __nv_bfloat16*>(w->wqkv[l]));
+    lm->wo.push_back(static_cast<const __nv_bfloat16*>(w->wo[l]));
+    lm->wgu.push_back(static_cast<const __nv_bfloat16*>(w->wgu[l]));
+    lm->wd.push_back(static_cast<const __nv_bfloat16*>(w->wd[l]));
+  }
+  int dev = 0;
+  cudaDeviceProp prop;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+    delete lm;
+    return set_error(NT_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  }
+  if (prop.major != 10) {
+    delete lm;
+    return set_error(NT_ERR_CUDA, "device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  }
+  lm->num_sms = prop.multiProcessorCount;
+  // rotary inverse frequencies (modeling_qwen2.py:95-100), iota, zeroed split counters
+  float invf[64] = {0};
+  for (int i = 0; i < 32; ++i) invf[i] = static_cast<float>(1.0 / std::pow(static_cast<double>(c.rope_theta), (2.0 * i) / 64.0));
+  std::vector<int> iota(c.max_batch);
+  for (int i = 0; i < c.max_batch; ++i) iota[i] = i;
+  if (cudaMemcpy(lm->inv_freq, invf, sizeof(invf), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(lm->iota, iota.data(), iota.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemset(lm->counters, 0, size_t(c.max_batch) * c.n_kv_heads * sizeof(int)) != cudaSuccess) {
+    delete lm;
+    return set_error(NT_ERR_CUDA, "workspace initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  *out = lm;
+  return NT_OK;
+}
+
+extern "C" int nt_lm_destroy(nt_lm* lm) {
+  if (!lm) return NT_OK;
+  if (lm->graph) cudaGraphExecDestroy(lm->graph);
+  delete lm;
+  return NT_OK;
+}
+
+static KVLayout make_kv(const nt_lm* lm, const nt_lm_state* st) {
+  const nt_lm_config& c = lm->cfg;
+  KVLayout kv;
+  kv.pages = static_cast<__nv_bfloat16*>(st->kv_pages);
+  kv.page_table = st->page_table;
+  kv.seq_lens = st->seq_lens;
+  kv.n_kv_heads = c.n_kv_heads;
+  kv.num_pages = c.num_pages;
+  kv.max_pages_per_seq = c.max_ctx / c.page_size;
+  kv.max_ctx = c.max_ctx;
+  kv.kv_stride = static_cast<long long>(c.num_pages) * c.n_kv_heads * 64 * 64;
+  kv.layer_stride = 2 * kv.kv_stride;
+  return kv;
+}
+
+static SamplerParams make_sampler(const nt_lm* lm, const nt_lm_state* st, const nt_sampling* sp) {
+  SamplerParams s;
+  memset(&s, 0, sizeof(s));
+  s.logits = lm->logits;
+  s.V = lm->cfg.vocab_size;
+  s.sp = *sp;
+  s.seq_lens = st->seq_lens;
+  s.cur_token = st->cur_token;
+  s.out_tokens = st->out_tokens;
+  s.n_generated = st->n_generated;
+  s.done = st->done;
+  s.max_new = st->max_new;
+  s.max_ctx = lm->cfg.max_ctx;
+  s.cand_val = lm->cand_val;
+  s.cand_idx = lm->cand_idx;
+  s.nchunks = lm->nchunks;
+  s.embed = lm->embed;
+  s.h = lm->h;
+  s.hidden = lm->cfg.hidden;
+  return s;
+}
+
+static int check_sampling(const nt_lm* lm, const nt_lm_state* st, const nt_sampling* sp) {
+  if (!sp) return set_error(NT_ERR_INVALID, "null sampling params");
+  if (sp->eos_id < 0 || sp->eos_id >= lm->cfg.vocab_size) return set_error(NT_ERR_INVALID, "eos_id out of range");
+  if (sp->max_new_tokens < 1 || sp->max_new_tokens > st->max_new)
+    return set_error(NT_ERR_INVALID, "max_new_tokens %d not in 1..%d", sp->max_new_tokens, st->max_new);
+  return NT_OK;
+}
+
+// lm_head on B hidden rows (fp32, un-normalised) -> lm->logits / `logits`
+static int lm_head_rows(nt_lm* lm, const float* hrows, int B, float* logits, cudaStream_t stream) {
+  const nt_lm_config& c = lm->cfg;
+  if (B <= 4) {
+    GemvParams g;
+    memset(&g, 0, sizeof(g));
+    g.W = lm->lm_head, g.rows = c.vocab_size, g.K = c.hidden;
+    g.x = hrows, g.ldx = c.hidden;
+    g.norm_w = lm->final_norm, g.eps = c.rms_eps;
+    g.epi = GEMV_STORE, g.out = logits, g.ldo = c.vocab_size;
+    return launch_gemv(g, B, lm->num_sms, stream);
+  }
+  int rc = launch_rmsnorm_rows(hrows, lm->final_norm, c.rms_eps, B, c.hidden, nullptr, lm->xn, stream);
+  if (rc) return rc;
+  nt_gemm_args a;
+  memset(&a, 0, sizeof(a));
+  a.dtype = NT_BF16, a.M = B, a.N = c.vocab_size, a.K = c.hidden;
+  a.A = lm->xn, a.lda = c.hidden, a.W = lm->lm_head, a.ldw = c.hidden;
+  a.out_f32 = logits, a.ldc = c.vocab_size;
+  return gemm_dispatch(a, stream);
+}
+
+// Transformer layers over `rows` token rows held in lm->h, via tensor-core GEMMs.
+// mode 0: prefill (causal attention over the prompt);  mode 1: one new token per sequence.
+static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mode, int max_len, cudaStream_t stream) {
+  const nt_lm_config& c = lm->cfg;
+  const KVLayout kv = make_kv(lm, st);
+  const int H = c.hidden, I = c.inter, QN = lm->qkv_n, HD = c.n_heads * 64;
+  const float scale_log2 = (1.0f / 8.0f) * 1.4426950408889634f;
+  int rc;
+  for (int l = 0; l < c.n_layers; ++l) {
+    if ((rc = launch_rmsnorm_rows(lm->h, lm->ln1[l], c.rms_eps, rows, H, nullptr, lm->xn, stream))) return rc;
+    nt_gemm_args a;
+    memset(&a, 0, sizeof(a));
+    a.dtype = NT_BF16, a.M = rows, a.N = QN, a.K = H, a.A = lm->xn, a.lda = H, a.W = lm->wqkv[l], a.ldw = H;
+    a.bias = lm->bqkv[l], a.out_f32 = lm->qkv, a.ldc = QN;
+    if ((rc = gemm_dispatch(a, stream))) return rc;
+    const int32_t* tseq = mode == 0 ? lm->tok_seq : lm->iota;
+    const int32_t* tpos = mode == 0 ? lm->tok_pos : st->seq_lens;
+    if ((rc = launch_rope_append(lm->qkv, rows, QN, tseq, tpos, c.n_heads, lm->inv_freq, lm->q, kv, l, stream))) return rc;
+    if (mode == 0) {
+      AttnPrefillParams ap;
+      ap.q = lm->q, ap.kv = kv, ap.layer = l, ap.n_heads = c.n_heads, ap.n_rep = c.n_heads / c.n_kv_heads;
+      ap.scale_log2 = scale_log2, ap.cu_seqlens = lm->cu_dev, ap.out = lm->attn_bf16, ap.max_len = max_len;
+      if ((rc = launch_attn_prefill(ap, B, stream))) return rc;
+    } else {
+      AttnDecParams ad;
+      ad.q = lm->q, ad.kv = kv, ad.layer = l, ad.n_heads = c.n_heads, ad.n_rep = c.n_heads / c.n_kv_heads;
+      ad.scale_log2 = scale_log2, ad.part_o = lm->part_o, ad.part_ml = lm->part_ml, ad.counters = lm->counters;
+      ad.out = lm->attn, ad.out_bf16 = lm->attn_bf16, ad.max_splits = lm->max_splits;
+      if ((rc = launch_attn_decode(ad, B, stream))) return rc;
+    }
+    memset(&a, 0, sizeof(a));
+    a.dtype = NT_BF16, a.M = rows, a.N = H, a.K = HD, a.A = lm->attn_bf16, a.lda = HD, a.W = lm->wo[l], a.ldw = HD;
+    a.residual = lm->h, a.ldr = H, a.out_f32 = lm->h, a.ldc = H;
+    if ((rc = gemm_dispatch(a, stream))) return rc;
+    if ((rc = launch_rmsnorm_rows(lm->h, lm->ln2[l], c.rms_eps, rows, H, nullptr, lm->xn, stream))) return rc;
+    memset(&a, 0, sizeof(a));
+    a.dtype = NT_BF16, a.M = rows, a.N = 2 * I, a.K = H, a.A = lm->xn, a.lda = H, a.W = lm->wgu[l], a.ldw = H;
+    a.act = NT_ACT_SWIGLU, a.out_bf16 = lm->act_bf16, a.ldc = I;
+    if ((rc = gemm_dispatch(a, stream))) return rc;
+    memset(&a, 0, sizeof(a));
+    a.dtype = NT_BF16, a.M = rows, a.N = H, a.K = I, a.A = lm->act_bf16, a.lda = I, a.W = lm->wd[l], a.ldw = I;
+    a.residual = lm->h, a.ldr = H, a.out_f32 = lm->h, a.ldc = H;
+    if ((rc = gemm_dispatch(a, stream))) return rc;
+  }
+  return NT_OK;
+}
+
+extern "C" int nt_lm_prefill(nt_lm* lm, const nt_lm_state* st, const int32_t* ids, const int32_t* cu, int B,
+                             const nt_sampling* sp, float* logits_out, void* stream_) {
+  if (!lm || !st || !ids || !cu) return set_error(NT_ERR_INVALID, "nt_lm_prefill: null argument");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const nt_lm_config& c = lm->cfg;
+  if (B < 1 || B > c.max_batch) return set_error(NT_ERR_INVALID, "batch %d not in 1..%d", B, c.max_batch);
+  int rc = check_sampling(lm, st, sp);
+  if (rc) return rc;
+  const int T = cu[B];
+  if (cu[0] != 0 || T < B || T > c.max_prefill_tokens)
+    return set_error(NT_ERR_INVALID, "prefill tokens %d not in %d..%d", T, B, c.max_prefill_tokens);
+  std::vector<int> tseq(T), tpos(T), last(B), lens(B);
+  int max_len = 0;
+  for (int b = 0; b < B; ++b) {
+    const int len = cu[b + 1] - cu[b];
+    if (len < 1 || len >= c.max_ctx) return set_error(NT_ERR_INVALID, "prompt %d has length %d (must be 1..%d)", b, len, c.max_ctx - 1);
+    for (int t = 0; t < len; ++t) tseq[cu[b] + t] = b, tpos[cu[b] + t] = t;
+    last[b] = cu[b + 1] - 1;
+    lens[b] = len;
+    if (len > max_len) max_len = len;
+  }
+  NT_CUDA_CHECK(cudaMemcpyAsync(lm->tok_seq, tseq.data(), T * sizeof(int), cudaMemcpyHostToDevice, stream));
+  NT_CUDA_CHECK(cudaMemcpyAsync(lm->tok_pos, tpos.data(), T * sizeof(int), cudaMemcpyHostToDevice, stream));
+  NT_CUDA_CHECK(cudaMemcpyAsync(lm->cu_dev, cu, (B + 1) * sizeof(int), cudaMemcpyHostToDevice, stream));
+  NT_CUDA_CHECK(cudaMemcpyAsync(lm->last_rows, last.data(), B * sizeof(int), cudaMemcpyHostToDevice, stream));
+  // host vectors above are pageable: the runtime stages them before returning, so they may go out of scope
+  if ((rc = launch_embed_rows(lm->embed, ids, T, c.hidden, lm->h, stream))) return rc;
+  if ((rc = layers_gemm(lm, st, T, B, 0, max_len, stream))) return rc;
+  if ((rc = launch_gather_rows(lm->h, lm->last_rows, B, c.hidden, lm->h_last, stream))) return rc;
+  if ((rc = lm_head_rows(lm, lm->h_last, B, lm->logits, stream))) return rc;
+  if (logits_out)
+    NT_CUDA_CHECK(cudaMemcpyAsync(logits_out, lm->logits, size_t(B) * c.vocab_size * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  NT_CUDA_CHECK(cudaMemcpyAsync(st->seq_lens, lens.data(), B * sizeof(int), cudaMemcpyHostToDevice, stream));
+  SamplerParams s = make_sampler(lm, st, sp);
+  if ((rc = launch_sampler(s, B, stream))) return rc;
+  lm->prefilled = true;
+  return NT_OK;
+}
+
+// one decode step for slots 0..B-1 (all launches asynchronous, PDL-chained)
+static int decode_step(nt_lm* lm, const nt_lm_state* st, int B, const nt_sampling* sp, cudaStream_t stream) {
+  const nt_lm_config& c = lm->cfg;
+  int rc;
+  if (B <= 4) {
+    const KVLayout kv = make_kv(lm, st);
+    const int H = c.hidden, I = c.inter, HD = c.n_heads * 64;
+    const float scale_log2 = (1.0f / 8.0f) * 1.4426950408889634f;
+    for (int l = 0; l < c.n_layers; ++l) {
+      GemvParams g;
+      memset(&g, 0, sizeof(g));
+      g.W = lm->wqkv[l], g.rows = lm->qkv_n, g.K = H, g.x = lm->h, g.ldx = H;
+      g.norm_w = lm->ln1[l], g.eps = c.rms_eps, g.bias = lm->bqkv[l];
+      g.epi = GEMV_QKV_ROPE, g.q_out = lm->q, g.kv = kv, g.layer = l, g.n_heads = c.n_heads, g.inv_freq = lm->inv_freq;
+      if ((rc = launch_gemv(g, B, lm->num_sms, stream))) return rc;
+
+      AttnDecParams ad;
+      ad.q = lm->q, ad.kv = kv, ad.layer = l, ad.n_heads = c.n_heads, ad.n_rep = c.n_heads / c.n_kv_heads;
+      ad.scale_log2 = scale_log2, ad.part_o = lm->part_o, ad.part_ml = lm->part_ml, ad.counters = lm->counters;
+      ad.out = lm->attn, ad.out_bf16 = nullptr, ad.max_splits = lm->max_splits;
+      if ((rc = launch_attn_decode(ad, B, stream))) return rc;
+
+      memset(&g, 0, sizeof(g));
+      g.W = lm->wo[l], g.rows = H, g.K = HD, g.x = lm->attn, g.ldx = HD;
+      g.epi = GEMV_STORE, g.out = lm->h, g.ldo = H, g.residual = lm->h, g.ldr = H;
+      if ((rc = launch_gemv(g, B, lm->num_sms, stream))) return rc;
+
+      memset(&g, 0, sizeof(g));
+      g.W = lm->wgu[l], g.rows = 2 * I, g.K = H, g.x = lm->h, g.ldx = H;
+      g.norm_w = lm->ln2[l], g.eps = c.rms_eps;
+      g.epi = GEMV_SWIGLU, g.out = lm->act, g.ldo = I;
+      if ((rc = launch_gemv(g, B, lm->num_sms, stream))) return rc;
+
+      memset(&g, 0, sizeof(g));
+      g.W = lm->wd[l], g.rows = H, g.K = I, g.x = lm->act, g.ldx = I;
+      g.epi = GEMV_STORE, g.out = lm->h, g.ldo = H, g.residual = lm->h, g.ldr = H;
+      if ((rc = launch_gemv(g, B, lm->num_sms, stream))) return rc;
+    }
+  } else {
+    if ((rc = layers_gemm(lm, st, B, B, 1, 0, stream))) return rc;
+  }
+  if ((rc = lm_head_rows(lm, lm->h, B, lm->logits, stream))) return rc;
+  SamplerParams s = make_sampler(lm, st, sp);
+  s.advance = 1;
+  return launch_sampler(s, B, stream);
+}
+
+extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps, const nt_sampling* sp,
+                            float* logits_out, void* stream_) {
+  if (!lm || !st) return set_error(NT_ERR_INVALID, "nt_lm_decode: null argument");
+  if (!lm->prefilled) return set_error(NT_ERR_STATE, "nt_lm_decode called before nt_lm_prefill");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const nt_lm_config& c = lm->cfg;
+  if (B < 1 || B > c.max_batch) return set_error(NT_ERR_INVALID, "batch %d not in 1..%d", B, c.max_batch);
+  int rc = check_sampling(lm, st, sp);
+  if (rc) return rc;
+  if (n_steps < 0) return set_error(NT_ERR_INVALID, "negative step count");
+
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  NT_CUDA_CHECK(cudaStreamIsCapturing(stream, &cap));
+  const bool use_graph = !logits_out && cap == cudaStreamCaptureStatusNone && !env_flag("NT_NO_GRAPH") && n_steps > 1;
+  if (!use_graph) {
+    for (int i = 0; i < n_steps; ++i) {
+      if ((rc = decode_step(lm, st, B, sp, stream))) return rc;
+      if (logits_out)
+        NT_CUDA_CHECK(cudaMemcpyAsync(logits_out + size_t(i) * B * c.vocab_size, lm->logits,
+                                      size_t(B) * c.vocab_size * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    }
+    return NT_OK;
+  }
+  // graph keyed by everything baked into the kernel parameters
+  std::vector<uint8_t> key(sizeof(int) + sizeof(nt_lm_state) + sizeof(nt_sampling));
+  memcpy(key.data(), &B, sizeof(int));
+  memcpy(key.data() + sizeof(int), st, sizeof(nt_lm_state));
+  memcpy(key.data() + sizeof(int) + sizeof(nt_lm_state), sp, sizeof(nt_sampling));
+  if (!lm->graph || key != lm->graph_key) {
+    if (lm->graph) {
+      cudaGraphExecDestroy(lm->graph);
+      lm->graph = nullptr;
+    }
+    cudaGraph_t g = nullptr;
+    NT_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    rc = decode_step(lm, st, B, sp, stream);
+    cudaError_t e = cudaStreamEndCapture(stream, &g);
+    if (rc) {
+      if (g) cudaGraphDestroy(g);
+      return rc;
+    }
+    if (e != cudaSuccess) return set_error(NT_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&lm->graph, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+      lm->graph = nullptr;
+      return set_error(NT_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    }
+    lm->graph_key = key;
+  }
+  for (int i = 0; i < n_steps; ++i) NT_CUDA_CHECK(cudaGraphLaunch(lm->graph, stream));
+  return NT_OK;
+}
+
+extern "C" int nt_lm_head_gemv(nt_lm* lm, const float* h, int B, float* logits, void* stream) {
+  if (!lm || !h || !logits) return set_error(NT_ERR_INVALID, "nt_lm_head_gemv: null argument");
+  if (B < 1 || B > 4) return set_error(NT_ERR_INVALID, "nt_lm_head_gemv: batch %d not in 1..4", B);
+  return lm_head_rows(lm, h, B, logits, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nt_op_rmsnorm(const float* x, const float* w, float eps, int rows, int cols, float* out_f32, void* out_bf16,
+                             void* stream) {
+  if (!x || !w || (!out_f32 && !out_bf16)) return set_error(NT_ERR_INVALID, "nt_op_rmsnorm: null argument");
+  return launch_rmsnorm_rows(x, w, eps, rows, cols, out_f32, static_cast<__nv_bfloat16*>(out_bf16),
+                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nt_op_topk_sample(const float* logits, int B, int V, const nt_sampling* sp, const int32_t* n_generated,
+                                 int32_t step, int32_t* out_token, float* out_topk_val, int32_t* out_topk_idx,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!logits || !sp || !n_generated || !workspace) return set_error(NT_ERR_INVALID, "nt_op_topk_sample: null argument");
+  Arena a(workspace, workspace_bytes);
+  SamplerParams s;
+  memset(&s, 0, sizeof(s));
+  s.logits = logits, s.V = V, s.sp = *sp;
+  s.nchunks = sampler_nchunks(V);
+  s.cand_val = a.take<float>(sampler_scratch_floats(B, V));
+  s.cand_idx = a.take<int>(sampler_scratch_floats(B, V));
+  if (!a.ok()) return set_error(NT_ERR_NOMEM, "nt_op_topk_sample: workspace too small (need %zu)", a.off);
+  s.n_generated_override = n_generated;
+  s.step_override = step;
+  s.dbg_token = out_token, s.dbg_topk_val = out_topk_val, s.dbg_topk_idx = out_topk_idx;
+  s.max_new = 1 << 30, s.max_ctx = 1 << 30;
+  return launch_sampler(s, B, reinterpret_cast<cudaStream_t>(stream));
+}

@@ -1,0 +1,70 @@
+"""GPU parity of the NeuCodec decoder path against the CPU restatement (oracle/codec_oracle.py).
+
+Bar (BASELINE.json north_star): PCM within 1e-3 RMS of the fp32 reference path.  The oracle is
+"parity unpinned" at the reference boundary (neucodec is not available offline) — these tests pin
+the CUDA path to the restatement, stage by stage and end to end."""
+import pytest
+import torch
+
+from oracle import codec_oracle as CO
+from tests.helpers import make_codec, max_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _rms(x):
+    return float(x.double().pow(2).mean().sqrt())
+
+
+@pytest.mark.parametrize("rope_axis", ["time", "head"])
+def test_codec_tiny_config(cuda, rope_axis):
+    cfg = CO.CodecConfig.tiny(rope_axis=rope_axis)
+    w = CO.random_weights(cfg, 3)
+    dec = make_codec(cfg, w, max_batch=3, max_frames=128)
+    g = torch.Generator().manual_seed(0)
+    codes = torch.randint(0, cfg.codebook_size, (3, 1, 77), generator=g)
+    with torch.no_grad():
+        ref = CO.decode_code(codes, w, cfg)
+    got = dec.decode_code(codes).cpu()
+    assert got.shape == ref.shape == (3, 1, cfg.hop * 77)
+    err = _rms(got - ref)
+    assert err < 1e-3 and err < 5e-3 * _rms(ref), (err, _rms(ref))
+
+
+def test_codec_full_size_dave_250(cuda):
+    """Full NeuCodec decoder shape, 250 frames (5 s) — the BASELINE workload; batch of 2 with
+    different codes to cover the padded-batch layout."""
+    cfg = CO.CodecConfig()
+    w = CO.random_weights(cfg, 0)
+    dec = make_codec(cfg, w, max_batch=2, max_frames=256)
+    g = torch.Generator().manual_seed(1)
+    codes = torch.randint(0, 65536, (2, 1, 250), generator=g)
+    with torch.no_grad():
+        ref = CO.decode_code(codes, w, cfg)
+    got = dec.decode_code(codes).cpu()
+    assert torch.isfinite(got).all()
+    err, level = _rms(got - ref), _rms(ref)
+    assert 0.02 < level < 0.5                       # speech-like level, so the absolute bar is meaningful
+    assert err < 1e-3, (err, level)
+    # batch invariance: item 0 alone gives the same samples
+    solo = dec.decode_code(codes[:1]).cpu()
+    assert max_err(solo[0], got[0]) < 1e-5
+
+
+def test_codec_edge_shapes(cuda):
+    cfg = CO.CodecConfig.tiny()
+    w = CO.random_weights(cfg, 4)
+    dec = make_codec(cfg, w, max_batch=2, max_frames=300)
+    for n in (1, 2, 5, 129, 300):                   # shorter than the STFT overlap, tile boundaries, max
+        codes = torch.randint(0, cfg.codebook_size, (1, 1, n), generator=torch.Generator().manual_seed(n))
+        with torch.no_grad():
+            ref = CO.decode_code(codes, w, cfg)
+        got = dec.decode_code(codes).cpu()
+        assert got.shape == (1, 1, cfg.hop * n)
+        assert _rms(got - ref) < 1e-3, n
+    with pytest.raises(ValueError):
+        dec.decode_code(torch.zeros(1, 1, 301, dtype=torch.long))
+    with pytest.raises(ValueError):
+        dec.decode_code(torch.full((1, 1, 4), cfg.codebook_size, dtype=torch.long))
+    with pytest.raises(ValueError):
+        dec.decode_code(torch.zeros(1, 4, dtype=torch.long))

@@ -1,0 +1,198 @@
+"""GPU parity tests of single kernels through the C-ABI (tcgen05 GEMM, RMSNorm, sampler).
+
+The comparison target for these float kernels is a plain PyTorch fp32 evaluation of the same
+op on the same (rounded) operands; tolerances are stated next to each assertion."""
+import ctypes as C
+
+import pytest
+import torch
+
+from tests.helpers import max_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(L, dtype, A, W, M=None, N=None, K=None, lda=None, bias=None, residual=None, act=0, out_f32=None, out_bf16=None,
+          ldc=None, valid=(0, 0)):
+    from neutts_air_b200 import _lib
+
+    M = M if M is not None else A.shape[0]
+    N = N if N is not None else W.shape[0]
+    K = K if K is not None else W.shape[1]
+    a = _lib.GemmArgs()
+    a.dtype, a.M, a.N, a.K = dtype, M, N, K
+    a.A, a.lda = A.data_ptr(), lda if lda is not None else A.stride(0)
+    a.W, a.ldw = W.data_ptr(), W.stride(0)
+    a.bias = bias.data_ptr() if bias is not None else None
+    a.residual = residual.data_ptr() if residual is not None else None
+    a.ldr = residual.stride(0) if residual is not None else 0
+    a.act = act
+    a.out_f32 = out_f32.data_ptr() if out_f32 is not None else None
+    a.out_bf16 = out_bf16.data_ptr() if out_bf16 is not None else None
+    a.ldc = ldc if ldc is not None else (out_f32 if out_f32 is not None else out_bf16).stride(0)
+    a.valid_period, a.valid_len = valid
+    _lib.check(L.nt_gemm(C.byref(a), _lib.current_stream_ptr()))
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (500, 896, 896), (500, 1152, 896), (7, 896, 4864), (300, 1922, 1024),
+                                   (1000, 9728, 896), (64, 2048, 896)])
+def test_gemm_bf16_plain(cuda, M, N, K):
+    from neutts_air_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g).bfloat16().to(cuda)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(cuda)
+    out = torch.full((M, N), float("nan"), device=cuda)
+    _gemm(L, _lib.NT_BF16, A, W, out_f32=out)
+    ref = A.float() @ W.float().T
+    # same bf16 operands, fp32 accumulation on both sides: only summation order differs
+    assert rel_err(out, ref) < 1e-5, (rel_err(out, ref), max_err(out, ref))
+
+
+def test_gemm_bf16_epilogues(cuda):
+    from neutts_air_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(3)
+    M, N, K = 333, 896, 896
+    A = torch.randn(M, K, generator=g).bfloat16().to(cuda)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16().to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    res = torch.randn(M, N, generator=g).to(cuda)
+    ref = A.float() @ W.float().T
+    # bias + residual, fp32 out aliasing the residual (the prefill o_proj/down_proj pattern)
+    out = res.clone()
+    _gemm(L, _lib.NT_BF16, A, W, bias=bias, residual=out, out_f32=out)
+    assert rel_err(out, ref + bias + res) < 1e-5
+    # SiLU + bf16 output
+    ob = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda)
+    _gemm(L, _lib.NT_BF16, A, W, act=_lib.NT_ACT_SILU, out_bf16=ob)
+    assert rel_err(ob.float(), torch.nn.functional.silu(ref)) < 4e-3      # bf16 output rounding
+    # SwiGLU over interleaved (gate, up) columns -> N/2 bf16 outputs
+    og = torch.zeros(M, N // 2, dtype=torch.bfloat16, device=cuda)
+    _gemm(L, _lib.NT_BF16, A, W, act=_lib.NT_ACT_SWIGLU, out_bf16=og, ldc=N // 2)
+    want = torch.nn.functional.silu(ref[:, 0::2]) * ref[:, 1::2]
+    assert rel_err(og.float(), want) < 4e-3
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 1024, 1024), (256, 1922, 1024), (250, 1920, 1922), (77, 3072, 1024)])
+def test_gemm_tf32(cuda, M, N, K):
+    from neutts_air_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(N)
+    ld = (K + 31) // 32 * 32
+    A = torch.zeros(M, ld)
+    W = torch.zeros(N, ld)
+    A[:, :K] = torch.randn(M, K, generator=g)
+    W[:, :K] = torch.randn(N, K, generator=g) / K ** 0.5
+    A, W = A.to(cuda), W.to(cuda)
+    out = torch.full((M, N), float("nan"), device=cuda)
+    _gemm(L, _lib.NT_TF32, A, W, K=K, out_f32=out)
+    ref = (A[:, :K].double() @ W[:, :K].double().T).float()
+    # tf32 operands (10-bit mantissa), fp32 accumulation: ~1e-3 relative
+    assert rel_err(out, ref) < 2e-3, rel_err(out, ref)
+
+
+def test_gemm_conv_taps_and_row_mask(cuda):
+    """Conv1d(k=3, pad=1) over a padded-batch layout expressed as one GEMM (codec path)."""
+    from neutts_air_b200 import _lib
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(5)
+    B, T, Cc, Co = 3, 50, 128, 96
+    Tp = T + 6
+    x = torch.randn(B, Cc, T, generator=g)
+    w = torch.randn(Co, Cc, 3, generator=g) / (3 * Cc) ** 0.5
+    b = torch.randn(Co, generator=g)
+    ref = torch.nn.functional.conv1d(x, w, b, padding=1)                      # [B, Co, T]
+    buf = torch.zeros(B * Tp + 8, Cc)
+    for i in range(B):
+        buf[i * Tp + 3: i * Tp + 3 + T] = x[i].T
+    buf = buf.to(cuda)
+    w2 = w.permute(0, 2, 1).reshape(Co, 3 * Cc).contiguous().to(cuda)
+    out = torch.zeros(B * Tp + 8, Co, device=cuda)
+    a_view = buf[2:]                                                           # first row the tap window of output row 0 touches
+    _gemm(L, _lib.NT_TF32, a_view, w2, M=B * Tp - 6, K=3 * Cc, lda=Cc, bias=b.to(cuda), out_f32=out[3:], valid=(Tp, T))
+    got = torch.stack([out[i * Tp + 3: i * Tp + 3 + T].T for i in range(B)]).cpu()
+    assert rel_err(got, ref) < 2e-3
+    pad_rows = torch.cat([out[i * Tp: i * Tp + 3] for i in range(B)] + [out[i * Tp + 3 + T: (i + 1) * Tp] for i in range(B)])
+    assert float(pad_rows.abs().max()) == 0.0                                  # masked rows were never written
+
+
+def test_rmsnorm_rows(cuda):
+    from neutts_air_b200 import _lib
+    from oracle.lm_oracle import rms_norm
+
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(37, 896, generator=g) * 3
+    w = 1 + 0.1 * torch.randn(896, generator=g)
+    xo = torch.empty(37, 896, device=cuda)
+    xb = torch.empty(37, 896, dtype=torch.bfloat16, device=cuda)
+    _lib.check(L.nt_op_rmsnorm(x.to(cuda).data_ptr(), w.to(cuda).data_ptr(), 1e-6, 37, 896, xo.data_ptr(), xb.data_ptr(),
+                               _lib.current_stream_ptr()))
+    torch.cuda.synchronize()
+    ref = rms_norm(x, w, 1e-6)
+    assert max_err(xo, ref) < 1e-5
+    assert max_err(xb.float(), ref.bfloat16().float()) < 4e-2   # one bf16 ulp at |x|~8
+
+
+def _sample(L, logits, sp, ngen, step):
+    from neutts_air_b200 import _lib
+
+    B, V = logits.shape
+    dev = logits.device
+    tok = torch.zeros(B, dtype=torch.int32, device=dev)
+    tv = torch.zeros(B, 64, device=dev)
+    ti = torch.zeros(B, 64, dtype=torch.int32, device=dev)
+    ws = torch.empty(1 << 24, dtype=torch.uint8, device=dev)
+    ng = torch.tensor(ngen, dtype=torch.int32, device=dev)
+    _lib.check(L.nt_op_topk_sample(logits.data_ptr(), B, V, C.byref(sp), ng.data_ptr(), step, tok.data_ptr(), tv.data_ptr(),
+                                   ti.data_ptr(), ws.data_ptr(), ws.numel(), _lib.current_stream_ptr()))
+    torch.cuda.synchronize()
+    return tok.cpu(), tv.cpu(), ti.cpu()
+
+
+def test_sampler_topk_set_eos_mask_and_distribution(cuda):
+    """logits_process.py:224-233 (EOS masked while n_generated < min_new_tokens), :296-299 (temperature),
+    :580-586 (top-k) and the multinomial draw of utils.py:2789-2791."""
+    from neutts_air_b200 import _lib
+    from oracle.lm_oracle import topk_probs
+
+    L = _lib.lib()
+    V, eos = 217472, 151670
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(2, V, generator=g) * 2
+    logits[:, eos] = 30.0                                   # EOS would dominate if not masked
+    sp = _lib.Sampling(eos, 50, 1 << 20, 50, 0.7, 1234, 0, None)
+    tok, tv, ti = _sample(L, logits.to(cuda), sp, [10, 60], 0)
+    for b, ngen in enumerate([10, 60]):
+        idx, p = topk_probs(logits[b], ngen, eos, 50, 0.7, 50)
+        assert ti[b, :50].tolist() == idx.tolist()          # exact top-50 set and order
+        assert (ti[b, 50:] == -1).all()
+        assert max_err(tv[b, :50], p) < 1e-5
+        assert (eos in ti[b, :50].tolist()) == (ngen >= 50)
+        assert int(tok[b]) in idx.tolist()
+    # chi-square of 20000 draws against the oracle distribution (RNG streams cannot match torch.multinomial)
+    idx, p = topk_probs(logits[0], 10, eos, 50, 0.7, 50)
+    counts = torch.zeros(50)
+    pos = {int(t): j for j, t in enumerate(idx)}
+    rep = logits[0:1].repeat(64, 1).to(cuda)
+    n = 0
+    for step in range(320):
+        t, _, _ = _sample(L, rep, sp, [10] * 64, step)      # slot index + step key the Philox counter
+        for x in t.tolist():
+            counts[pos[x]] += 1
+            n += 1
+    exp = p * n
+    keep = exp > 5
+    chi2 = float(((counts[keep] - exp[keep]) ** 2 / exp[keep]).sum())
+    dof = int(keep.sum()) - 1
+    assert chi2 < dof + 5 * (2 * dof) ** 0.5, (chi2, dof)
+    # greedy
+    spg = _lib.Sampling(eos, 0, 1 << 20, 50, 1.0, 0, 1, None)
+    tok, _, _ = _sample(L, logits.to(cuda), spg, [0, 0], 0)
+    assert tok.tolist() == [eos, eos]
