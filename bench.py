@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Headline benchmark: NeuTTS-Air synthetic 500-prefill / 250-decode utterances -> 24 kHz PCM.
+
+    python bench.py --gpus N --steps K --warmup W            # B200 path (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's PyTorch CPU path
+
+One "step" = one pass of the hot path over one batch of utterances per GPU: prefill(500) ->
+250 decode steps (EOS masked until 250, top-k 50 / T=1 sampling on device) -> NeuCodec decode
+to 5.0 s of 24 kHz PCM.  Metric (BASELINE.json): audio-seconds per wall-second, whole job.
+Prints ONE JSON line on rank 0.  Synthetic data, seeded random weights at the inferred
+NeuTTS-Air / NeuCodec shapes (no checkpoints exist offline) — see DESIGN.md §measurement.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PREFILL, DECODE, HOP, SR = 500, 250, 480, 24000
+AUDIO_S = DECODE * HOP / SR  # 5.0 s per utterance
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=1, help="utterances per GPU per step (metric is quoted at 1, 8, 64)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also report batch 8 and 64 on this GPU under 'batches'")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic model + workload (identical on every rank and for both arms)
+# ----------------------------------------------------------------------------------------------
+def synth_prompts(n, vocab, speech_base, seed):
+    """128 uniform text ids + 372 speech ids (dave.pt-shaped reference), P = 500."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        text = torch.randint(0, 151643, (PREFILL - 372,), generator=g)
+        ref = speech_base + torch.randint(0, 65536, (372,), generator=g)
+        out.append(torch.cat((text, ref)).tolist())
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU path (transformers generate + codec restatement)
+# ----------------------------------------------------------------------------------------------
+def reference_components(n_decode, threads=None):
+    """Times prefill, decode (tok/s) and codec on the host cores with the reference's code path:
+    transformers Qwen2ForCausalLM.generate in fp32 (what transformers 4.56.1 loads by default at
+    neutts/neutts.py:164) + the fp32 PyTorch NeuCodec decoder restatement (oracle/codec_oracle.py)."""
+    from neutts_air_b200 import synthetic
+    from neutts_air_b200.codec import CodecShape
+    from oracle import codec_oracle as CO
+    from oracle import lm_oracle as LO
+
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = LO.LMConfig()
+    w = LO.LMWeights(embed=None)
+    sd = {k: v.float() for k, v in synthetic.lm_state_dict(cfg, 0).items()}   # same bf16-valued weights as the GPU arm
+    w.embed, w.final_norm, w.lm_head = sd["model.embed_tokens.weight"], sd["model.norm.weight"], sd["model.embed_tokens.weight"]
+    for i in range(cfg.num_layers):
+        p = f"model.layers.{i}."
+        w.layers.append(dict(ln1=sd[p + "input_layernorm.weight"], ln2=sd[p + "post_attention_layernorm.weight"],
+                             wq=sd[p + "self_attn.q_proj.weight"], bq=sd[p + "self_attn.q_proj.bias"],
+                             wk=sd[p + "self_attn.k_proj.weight"], bk=sd[p + "self_attn.k_proj.bias"],
+                             wv=sd[p + "self_attn.v_proj.weight"], bv=sd[p + "self_attn.v_proj.bias"],
+                             wo=sd[p + "self_attn.o_proj.weight"], wg=sd[p + "mlp.gate_proj.weight"],
+                             wu=sd[p + "mlp.up_proj.weight"], wd=sd[p + "mlp.down_proj.weight"]))
+    model = LO.to_hf_model(cfg, w, attn_implementation="sdpa")
+    speech_base, eos = 151936, 151670
+    prompt = torch.tensor(synth_prompts(1, cfg.vocab_size, speech_base, 1234)[0])[None]
+    ccfg = CO.CodecConfig()
+    cd = synthetic.codec_weights(CodecShape(), 0)
+    cw = CO.CodecWeights(**{k: cd[k] for k in ("project_out_w", "project_out_b", "fc_post_a_w", "fc_post_a_b", "embed_w", "embed_b",
+                                               "prior", "blocks", "post", "final_ln_w", "final_ln_b", "head_w", "head_b")})
+    codes = torch.randint(0, 65536, (1, 1, DECODE), generator=torch.Generator().manual_seed(7))
+
+    def run(n_new):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            model.generate(prompt, max_length=2048, eos_token_id=eos, do_sample=True, temperature=1.0, top_k=50, use_cache=True,
+                           min_new_tokens=n_new, max_new_tokens=n_new, pad_token_id=eos)
+        return time.perf_counter() - t0
+
+    return dict(run=run, codec=lambda: _timeit(lambda: CO.decode_code(codes, cw, ccfg)), cfg=cfg)
+
+
+def _timeit(fn):
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        fn()
+    return time.perf_counter() - t0
+
+
+def reference_measure(steps, warmup):
+    """Returns (audio-s/s, ms per utterance, sample description, cores)."""
+    cores = os.cpu_count() or 1
+    comp = reference_components(DECODE)
+    t1 = comp["run"](1)                      # warm-up + prefill-dominated time
+    t_short = comp["run"](17)
+    per_tok = max((t_short - t1) / 16, 1e-4)
+    est_full = t1 + per_tok * (DECODE - 1)
+    t_codec = comp["codec"]()
+    t_codec = comp["codec"]()
+    if est_full * (steps + warmup) <= 240:   # the whole arm stays within a few minutes: run the real workload
+        for _ in range(warmup):
+            comp["run"](DECODE)
+        ts = [comp["run"](DECODE) + comp["codec"]() for _ in range(steps)]
+        t = float(np.mean(ts))
+        sample = f"full workload x{steps}: generate(500->750, fp32, sdpa) + codec restatement(250 frames), {torch.get_num_threads()} threads"
+    else:
+        t = est_full + t_codec
+        sample = (f"bounded sample: prefill(500)+1 tok = {t1:.2f}s, 16 decode tokens -> {per_tok * 1e3:.1f} ms/token, codec(250) = "
+                  f"{t_codec:.2f}s; composed to 250 tokens, {torch.get_num_threads()} threads")
+    return AUDIO_S / t, t * 1e3, sample, cores, dict(prefill_s=t1, ms_per_token=per_tok * 1e3, codec_s=t_codec,
+                                                      decode_tok_s=1.0 / per_tok)
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    v, ms, sample, cores, parts = reference_measure(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "audio-sec/sec (RTF), NeuTTS-Air 500 prefill / 250 decode + NeuCodec decode", "value": v,
+        "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: 1 utterance, 500 prefill / 250 decode tokens, batch=1, NeuCodec decode to 24 kHz",
+                   "note": "reference never batches (neutts/neutts.py:335); CPU path = transformers generate fp32 + codec restatement"},
+        "cpu_baseline": {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample, **parts},
+        "e2e": {"value": v, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+def build_engines(device, batch):
+    from neutts_air_b200 import synthetic
+    from neutts_air_b200.codec import CodecDecoder, CodecShape
+    from neutts_air_b200.lm import LMShape, SpeechLM
+
+    shape = LMShape()
+    lm = SpeechLM(shape, synthetic.lm_state_dict(shape, 0), device=device, max_batch=batch, max_ctx=2048, max_new=256,
+                  max_prefill_tokens=batch * PREFILL)
+    codec = CodecDecoder(CodecShape(), synthetic.codec_weights(CodecShape(), 0), device=device, max_batch=batch, max_frames=256)
+    return lm, codec
+
+
+def main_b200(args):
+    import torch.distributed as td
+
+    from neutts_air_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    B = args.batch
+    lm, codec = build_engines(dev, B)
+    speech_base, eos = 151936, 151670
+    prompts = synth_prompts(B, lm.shape.vocab_size, speech_base, 1234 + rank)
+    pinned_ids = torch.tensor([t for p in prompts for t in p], dtype=torch.int32).pin_memory()
+    lens = [len(p) for p in prompts]
+    h2d_bytes = pinned_ids.numel() * 4
+    pcm_host = torch.empty(B, DECODE * HOP, dtype=torch.float32).pin_memory()
+    d2h_bytes = pcm_host.numel() * 4
+
+    def codes_from(lm_):
+        c = lm_.out_tokens[:B, :DECODE].long() - speech_base
+        return c.clamp_(0, 65535)[:, None, :]       # random-weight LM may emit text ids; keep the codec input in range
+
+    def step_device(seed):
+        """inputs already resident in HBM; returns PCM on device."""
+        sp = lm.sampling(eos, min_new_tokens=DECODE, max_new_tokens=DECODE, top_k=50, temperature=1.0, seed=seed)
+        lm.prefill(prompts, sp)
+        lm.decode(DECODE - 1, sp)
+        return codec.decode_code(codes_from(lm))
+
+    def step_e2e(seed):
+        """host ids (pinned) -> H2D -> hot path -> D2H PCM (pinned): the call a user makes, minus the text front-end."""
+        sp = lm.sampling(eos, min_new_tokens=DECODE, max_new_tokens=DECODE, top_k=50, temperature=1.0, seed=seed)
+        lm.prefill_packed(pinned_ids, lens, sp)      # H2D copy of the prompt ids from pinned memory happens in here
+        lm.decode(DECODE - 1, sp)
+        pcm = codec.decode_code(codes_from(lm))
+        pcm_host.copy_(pcm[:, 0, :], non_blocking=True)
+        torch.cuda.synchronize()
+        return pcm_host
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+
+    def gather(pcm):
+        if world > 1:   # the one collective of the path: all-gather of finished waveforms
+            out = torch.empty(world * pcm.shape[0], pcm.shape[2], device=dev)
+            td.all_gather_into_tensor(out, pcm[:, 0, :].contiguous())
+            return out
+        return pcm
+
+    for i in range(args.warmup):
+        gather(step_device(i))
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    n0 = L.nt_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        gather(step_device(100 + i))
+    ev1.record()
+    barrier()
+    t_dev = ev0.elapsed_time(ev1) / 1e3
+    launches = L.nt_launch_count() - n0
+    clk = clocks.stop() if rank == 0 else None
+
+    # decode-only tokens/s (LM only, generated tokens / decode-loop time)
+    sp = lm.sampling(eos, min_new_tokens=DECODE, max_new_tokens=DECODE, seed=5)
+    lm.prefill(prompts, sp)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lm.decode(DECODE - 1, sp)
+    e1.record()
+    torch.cuda.synchronize()
+    t_dec = e0.elapsed_time(e1) / 1e3
+    e0.record()
+    lm.prefill(prompts, sp)
+    e1.record()
+    torch.cuda.synchronize()
+    t_pre = e0.elapsed_time(e1) / 1e3
+    e0.record()
+    codec.decode_code(codes_from(lm))
+    e1.record()
+    torch.cuda.synchronize()
+    t_codec = e0.elapsed_time(e1) / 1e3
+
+    # end-to-end through host buffers
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(200 + i)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    # roofline of the dominant kernel: lm_head GEMV (V x H bf16 = 390 MB > 126 MB L2, so every launch streams from HBM)
+    roof = None
+    if B <= 4:
+        h = torch.randn(B, lm.shape.hidden_size, device=dev)
+        for _ in range(3):
+            lm.head_gemv(h)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            lm.head_gemv(h)
+        e1.record()
+        torch.cuda.synchronize()
+        t_k = e0.elapsed_time(e1) / 1e3 / reps
+        alg = lm.shape.vocab_size * lm.shape.hidden_size * 2 + B * (lm.shape.hidden_size * 4 + lm.shape.vocab_size * 4)
+        peak, how = peaks()
+        roof = {"bound": "hbm", "kernel": "gemv_kernel<lm_head>", "achieved": alg / t_k / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg / t_k / 1e9 / peak, "traffic": None, "peak_source": how, "us_per_launch": t_k * 1e6,
+                "algorithmic_bytes": alg}
+
+    times = torch.tensor([t_dev, t_e2e, t_dec, t_pre, t_codec], device=dev, dtype=torch.float64)
+    if world > 1:
+        td.all_reduce(times, op=td.ReduceOp.MAX)
+    t_dev, t_e2e, t_dec, t_pre, t_codec = times.tolist()
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+    total_audio = AUDIO_S * B * world * args.steps
+    # algorithmic bytes of one decode step, averaged over contexts 500..749
+    cfgs = lm.shape
+    p_blk = cfgs.num_layers * ((cfgs.num_heads + 2 * cfgs.num_kv_heads) * 64 * (cfgs.hidden_size + 1) + cfgs.hidden_size * cfgs.num_heads * 64
+                               + 3 * cfgs.hidden_size * cfgs.intermediate_size + 2 * cfgs.hidden_size) + cfgs.hidden_size
+    step_bytes = 2 * (p_blk + cfgs.vocab_size * cfgs.hidden_size) + B * (12288 * (PREFILL + DECODE / 2 + 1) + 2 * cfgs.hidden_size)
+    peak, how = peaks()
+    line = {
+        "metric": "audio-sec/sec (RTF), NeuTTS-Air 500 prefill / 250 decode + NeuCodec decode",
+        "value": total_audio / t_dev, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 weights+KV / f32 accumulate (LM), tf32 tensor cores (codec)", "data": "synthetic",
+        "config": {"workload": f"configs[1]: 500 prefill / 250 decode tokens + NeuCodec decode to 24 kHz, batch={B} per GPU",
+                   "per_gpu_batch": B, "global_batch": B * world, "sharding": "utterances one-per-GPU-slot, weights replicated, "
+                   "one all-gather of waveforms" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2: 1.1 GB of weights stream per decode step (L2 = 126 MB)", "weights": "seeded random, inferred Air/NeuCodec shapes"},
+        "decode_tok_s": B * world * (DECODE - 1) / t_dec,
+        "decode_step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes * (DECODE - 1) / t_dec / 1e9,
+                                 "frac": step_bytes * (DECODE - 1) / t_dec / 1e9 / peak, "peak_source": how},
+        "breakdown_ms": {"prefill": t_pre * 1e3, "decode_249_steps": t_dec * 1e3, "codec": t_codec * 1e3},
+        "e2e": {"value": total_audio / t_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                "ms_per_step": t_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+    }
+    if roof:
+        line["roofline"] = roof
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            v, ms, sample, cores, parts = reference_measure(1, 0)
+            line["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample, **parts}
+        except Exception as e:  # the baseline must never take the GPU number down with it
+            line["cpu_baseline"] = {"value": None, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
+    print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        main_b200(a)

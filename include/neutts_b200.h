@@ -157,6 +157,12 @@ int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps, const nt_
  * exactly as the decode step launches it.  h: f32 [B][hidden] -> logits f32 [B][vocab]. */
 int nt_lm_head_gemv(nt_lm* lm, const float* h, int B, float* logits, void* stream);
 
+/* Per-stage parity hooks (tests): run only the first n_layers layers (-1 = all), and look up an
+ * internal activation buffer by name ("h", "q", "qkv", "attn", "act", "logits", "xn", "attn_bf16",
+ * "act_bf16", "h_last"); the pointer lies inside the caller's workspace. */
+int nt_lm_debug_set_layers(nt_lm* lm, int n_layers);
+void* nt_lm_debug_ptr(nt_lm* lm, const char* name);
+
 /* ------------------------------------------------------------------------------------------
  * NeuCodec decoder (seam 2)
  * ------------------------------------------------------------------------------------------ */

@@ -18,7 +18,7 @@ LIB = PKG / "libneutts_b200.so"
 SOURCES = ["lm_api.cu", "lm_kernels.cu", "gemm_tc.cu", "codec.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",
     "-Xcompiler", "-Wall",
 ]
 

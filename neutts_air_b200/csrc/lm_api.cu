@@ -48,7 +48,11 @@ struct nt_lm {
   // cached decode-step graph
   cudaGraphExec_t graph = nullptr;
   std::vector<uint8_t> graph_key;
+  cudaStream_t cap_stream = nullptr;  // capture happens here (torch's default stream is the legacy
+                                      // stream, which cannot be captured); replay on the caller's stream
+  uint64_t graph_kernels = 0;         // kernel nodes in the captured step (for nt_launch_count)
   bool prefilled = false;
+  int debug_layers = -1;              // >= 0: run only this many layers (per-stage parity tests)
 };
 
 template <typename F>
@@ -163,6 +167,10 @@ extern "C" int nt_lm_create(const nt_lm_config* cfg, const nt_lm_weights* w, voi
     delete lm;
     return set_error(NT_ERR_CUDA, "workspace initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
+  if (cudaStreamCreateWithFlags(&lm->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete lm;
+    return set_error(NT_ERR_CUDA, "stream creation failed");
+  }
   *out = lm;
   return NT_OK;
 }
@@ -170,6 +178,7 @@ extern "C" int nt_lm_create(const nt_lm_config* cfg, const nt_lm_weights* w, voi
 extern "C" int nt_lm_destroy(nt_lm* lm) {
   if (!lm) return NT_OK;
   if (lm->graph) cudaGraphExecDestroy(lm->graph);
+  if (lm->cap_stream) cudaStreamDestroy(lm->cap_stream);
   delete lm;
   return NT_OK;
 }
@@ -249,7 +258,8 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
   const int H = c.hidden, I = c.inter, QN = lm->qkv_n, HD = c.n_heads * 64;
   const float scale_log2 = (1.0f / 8.0f) * 1.4426950408889634f;
   int rc;
-  for (int l = 0; l < c.n_layers; ++l) {
+  const int n_layers = lm->debug_layers >= 0 ? lm->debug_layers : c.n_layers;
+  for (int l = 0; l < n_layers; ++l) {
     if ((rc = launch_rmsnorm_rows(lm->h, lm->ln1[l], c.rms_eps, rows, H, nullptr, lm->xn, stream))) return rc;
     nt_gemm_args a;
     memset(&a, 0, sizeof(a));
@@ -335,7 +345,8 @@ static int decode_step(nt_lm* lm, const nt_lm_state* st, int B, const nt_samplin
     const KVLayout kv = make_kv(lm, st);
     const int H = c.hidden, I = c.inter, HD = c.n_heads * 64;
     const float scale_log2 = (1.0f / 8.0f) * 1.4426950408889634f;
-    for (int l = 0; l < c.n_layers; ++l) {
+    const int n_layers = lm->debug_layers >= 0 ? lm->debug_layers : c.n_layers;
+    for (int l = 0; l < n_layers; ++l) {
       GemvParams g;
       memset(&g, 0, sizeof(g));
       g.W = lm->wqkv[l], g.rows = lm->qkv_n, g.K = H, g.x = lm->h, g.ldx = H;
@@ -408,9 +419,12 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
       lm->graph = nullptr;
     }
     cudaGraph_t g = nullptr;
-    NT_CUDA_CHECK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-    rc = decode_step(lm, st, B, sp, stream);
-    cudaError_t e = cudaStreamEndCapture(stream, &g);
+    const uint64_t before = g_launches.load();
+    NT_CUDA_CHECK(cudaStreamBeginCapture(lm->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = decode_step(lm, st, B, sp, lm->cap_stream);
+    cudaError_t e = cudaStreamEndCapture(lm->cap_stream, &g);
+    lm->graph_kernels = g_launches.load() - before;  // recorded, not executed: counted per replay instead
+    g_launches.store(before);
     if (rc) {
       if (g) cudaGraphDestroy(g);
       return rc;
@@ -424,8 +438,32 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
     }
     lm->graph_key = key;
   }
-  for (int i = 0; i < n_steps; ++i) NT_CUDA_CHECK(cudaGraphLaunch(lm->graph, stream));
+  for (int i = 0; i < n_steps; ++i) {
+    NT_CUDA_CHECK(cudaGraphLaunch(lm->graph, stream));
+    g_launches.fetch_add(lm->graph_kernels, std::memory_order_relaxed);
+  }
   return NT_OK;
+}
+
+// Debug / per-stage parity hooks: limit the number of layers run (-1 = all) and expose the
+// internal activation buffers (device pointers into the caller's workspace).
+extern "C" int nt_lm_debug_set_layers(nt_lm* lm, int n_layers) {
+  if (!lm || n_layers > lm->cfg.n_layers) return set_error(NT_ERR_INVALID, "nt_lm_debug_set_layers: bad argument");
+  lm->debug_layers = n_layers;
+  if (lm->graph) {
+    cudaGraphExecDestroy(lm->graph);
+    lm->graph = nullptr;
+  }
+  return NT_OK;
+}
+extern "C" void* nt_lm_debug_ptr(nt_lm* lm, const char* name) {
+  if (!lm || !name) return nullptr;
+  const struct { const char* n; void* p; } tab[] = {
+      {"h", lm->h}, {"q", lm->q}, {"qkv", lm->qkv}, {"attn", lm->attn}, {"act", lm->act}, {"logits", lm->logits},
+      {"xn", lm->xn}, {"attn_bf16", lm->attn_bf16}, {"act_bf16", lm->act_bf16}, {"h_last", lm->h_last}};
+  for (const auto& e : tab)
+    if (!strcmp(e.n, name)) return e.p;
+  return nullptr;
 }
 
 extern "C" int nt_lm_head_gemv(nt_lm* lm, const float* h, int B, float* logits, void* stream) {

@@ -150,6 +150,7 @@ class SpeechLM:
                                   self.cur_token.data_ptr(), self.out_tokens.data_ptr(), self.n_generated.data_ptr(),
                                   self.done.data_ptr(), self.max_new)
         self.pool = PagePool(self.num_pages, page_shuffle_seed)
+        self._table_host = None
         self._slot_pages = [[] for _ in range(max_batch)]
 
     def __del__(self):
@@ -174,10 +175,22 @@ class SpeechLM:
 
     def prefill(self, prompts, sp, return_logits: bool = False):
         """prompts: list of 1-D int sequences.  Fills the KV cache and samples the first token."""
-        B = len(prompts)
+        lens = [len(p) for p in prompts]
+        if not lens or min(lens) < 1:
+            raise ValueError("empty prompt")
+        flat = np.concatenate([np.asarray(p, dtype=np.int64) for p in prompts])
+        if flat.min() < 0 or flat.max() >= self.shape.vocab_size:
+            raise ValueError("token id out of range")
+        return self.prefill_packed(torch.from_numpy(flat.astype(np.int32)), lens, sp, return_logits)
+
+    def prefill_packed(self, ids_host: torch.Tensor, lens, sp, return_logits: bool = False):
+        """ids_host: int32 host tensor (pinned memory makes the H2D copy asynchronous) holding the
+        prompts back to back; lens: their lengths."""
+        B = len(lens)
         if not 1 <= B <= self.max_batch:
             raise ValueError(f"batch {B} not in 1..{self.max_batch}")
-        lens = [len(p) for p in prompts]
+        if ids_host.dtype != torch.int32 or ids_host.numel() != sum(lens):
+            raise ValueError("ids_host must be int32 with sum(lens) elements")
         for b in range(self.max_batch):
             if self._slot_pages[b]:
                 self.pool.release(self._slot_pages[b])
@@ -192,12 +205,11 @@ class SpeechLM:
             table[b, :need] = pages
         cu = np.zeros(B + 1, dtype=np.int32)
         cu[1:] = np.cumsum(lens)
-        flat = np.concatenate([np.asarray(p, dtype=np.int64) for p in prompts])
-        if flat.min() < 0 or flat.max() >= self.shape.vocab_size:
-            raise ValueError("token id out of range")
         with torch.cuda.device(self.device):
-            ids = torch.from_numpy(flat.astype(np.int32)).to(self.device)
-            self.page_table.copy_(torch.from_numpy(table))
+            ids = ids_host.to(self.device, non_blocking=True)
+            if self._table_host is None or not np.array_equal(self._table_host, table):
+                self.page_table.copy_(torch.from_numpy(table))
+                self._table_host = table
             self.n_generated.zero_()
             self.done.zero_()
             logits = torch.empty(B, self.shape.vocab_size, dtype=torch.float32, device=self.device) if return_logits else None
@@ -222,6 +234,19 @@ class SpeechLM:
         logits = torch.empty(B, self.shape.vocab_size, dtype=torch.float32, device=self.device)
         _lib.check(self.L.nt_lm_head_gemv(self.handle, h.data_ptr(), B, logits.data_ptr(), _lib.current_stream_ptr()))
         return logits
+
+    # ------------------------------------------------------------------ per-stage parity hooks (tests)
+    def debug_set_layers(self, n: int) -> None:
+        _lib.check(self.L.nt_lm_debug_set_layers(self.handle, n))
+
+    def debug_buffer(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        """View of an internal activation buffer (lives inside ``self.workspace``)."""
+        ptr = self.L.nt_lm_debug_ptr(self.handle, name.encode())
+        if not ptr:
+            raise KeyError(name)
+        off = ptr - self.workspace.data_ptr()
+        n = int(np.prod(shape)) * torch.empty(0, dtype=dtype).element_size()
+        return self.workspace[off: off + n].view(dtype).view(*shape)
 
     # ------------------------------------------------------------------ generation
     def generate_batch(self, prompts, eos_token_id: int, max_length: int | None = None, min_new_tokens: int = 50,

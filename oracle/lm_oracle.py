@@ -146,7 +146,7 @@ class KVCache:
 
 
 def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | None = None,
-            collect_hidden: bool = False, mirror: str | None = None):
+            collect_hidden: bool = False, mirror: str | None = None, collect: dict | None = None):
     """One sequence.  ids: int64 [T] (prompt for prefill, one id for a decode step).
     Follows Qwen2Model.forward modeling_qwen2.py:353-413 and the decoder layer
     :280-309 (pre-norm, residual add after attention and after the MLP); the
@@ -188,9 +188,13 @@ def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | Non
         a = attention(q, kk, vv, causal_offset=past, n_rep=n_rep)  # :231
         a = rb(a.reshape(T, -1))
         h = h + a @ L["wo"].T                                      # :244, :302
+        h_mid = h
         x = rb(rms_norm(h, L["ln2"], cfg.rms_eps))                 # :306
         act = torch.nn.functional.silu(x @ L["wg"].T) * (x @ L["wu"].T)  # :47
         h = h + rb(act) @ L["wd"].T                                # :308
+        if collect is not None:
+            collect[li] = dict(q=q.reshape(T, -1).clone(), k=k.clone(), v=v.clone(), attn=a.clone(),
+                               h_mid=h_mid.clone(), act=rb(act).clone(), h=h.clone())
         if collect_hidden:
             hiddens.append(h.clone())
     hn = rms_norm(h, w.final_norm, cfg.rms_eps)                    # :409

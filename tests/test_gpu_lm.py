@@ -119,3 +119,41 @@ def test_hf_generate_seam(cuda):
     assert out[0, :40].tolist() == list(range(40))
     with pytest.raises(ValueError):
         lm.generate(torch.arange(200)[None], max_length=128, eos_token_id=3)
+
+
+def _kv_rows(lm, layer, which, b, T):
+    """K or V of slot b, positions 0..T-1, gathered through the page table -> [T, n_kv, 64] fp32."""
+    table = lm.page_table[b].cpu().tolist()
+    pages = torch.stack([lm.kv[layer, which, table[t // 64], :, t % 64, :] for t in range(T)])
+    return pages.float().cpu()
+
+
+@pytest.mark.parametrize("cfgkw,P", [(SMALL, 70), (WIDE, 130)])
+def test_lm_prefill_stages_vs_oracle(cuda, cfgkw, P):
+    """Per-stage parity of the tensor-core prefill path, layer by layer:
+    q after RoPE, cached K/V, attention output, SwiGLU output, residual stream."""
+    cfg, w, lm = _setup(cfgkw, 61, max_batch=1, max_ctx=256, page_shuffle_seed=1)
+    g = torch.Generator().manual_seed(8)
+    prompt = torch.randint(0, cfg.vocab_size, (P,), generator=g)
+    col = {}
+    O.forward(cfg, w, prompt, O.KVCache(cfg.num_layers), mirror="prefill", collect=col)
+    sp = lm.sampling(cfg.vocab_size - 1, min_new_tokens=0, max_new_tokens=4)
+    errs = {}
+    HD, I, H = cfg.num_heads * 64, cfg.intermediate_size, cfg.hidden_size
+    for nl in range(1, cfg.num_layers + 1):
+        lm.debug_set_layers(nl)
+        lm.prefill([prompt.tolist()], sp)
+        torch.cuda.synchronize()
+        o, li = col[nl - 1], nl - 1
+        sc = lambda t: float(t.abs().max())
+        errs[f"L{li}.q"] = max_err(lm.debug_buffer("q", (P, HD)), o["q"]) / sc(o["q"])
+        errs[f"L{li}.k"] = max_err(_kv_rows(lm, li, 0, 0, P), o["k"]) / sc(o["k"])
+        errs[f"L{li}.v"] = max_err(_kv_rows(lm, li, 1, 0, P), o["v"]) / sc(o["v"])
+        errs[f"L{li}.attn"] = max_err(lm.debug_buffer("attn_bf16", (P, HD), torch.bfloat16).float(), o["attn"]) / sc(o["attn"])
+        errs[f"L{li}.act"] = max_err(lm.debug_buffer("act_bf16", (P, I), torch.bfloat16).float(), o["act"]) / sc(o["act"])
+        errs[f"L{li}.h"] = max_err(lm.debug_buffer("h", (P, H))[1:], o["h"][1:]) / sc(o["h"])  # row 0 reused by the sampler
+    lm.debug_set_layers(-1)
+    print("prefill stage errors (max abs / max |ref|):", {k: f"{v:.2e}" for k, v in errs.items()})
+    # bf16-stored stages may differ by one bf16 ulp (2^-8 relative) where a rounding flips
+    bad = {k: v for k, v in errs.items() if v > (8e-3 if k.split(".")[1] in ("k", "v", "attn", "act") else 2e-3)}
+    assert not bad, bad
