@@ -293,7 +293,9 @@ class NeuTTS:
             cache += self._ids_to_codes(new).tolist()
             while len(cache) - n_dec >= F + LA:
                 t0 = max(n_dec - LB - OV, 0)
-                t1 = n_dec + F + LA + OV
+                # the reference slices up to n_dec + F + LA + OV, but tokens arrive one at a time there, so
+                # its cache never holds more than n_dec + F + LA entries when a chunk fires (:401-415)
+                t1 = n_dec + F + LA
                 s0 = (n_dec - t0) * hop
                 wav = self._watermark(self._decode(cache[t0:t1]))[s0: s0 + (F + 2 * OV) * hop]
                 n_dec += F

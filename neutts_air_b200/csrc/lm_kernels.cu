@@ -497,13 +497,128 @@ NT_DEVINL void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
 
 constexpr int kTopChunk = 2048;
 constexpr int kTopKeep = 64;
+constexpr int kSelThreads = 256;
 
 int sampler_nchunks(int V) { return (V + kTopChunk - 1) / kTopChunk; }
 size_t sampler_scratch_floats(int B, int V) { return size_t(B) * sampler_nchunks(V) * kTopKeep; }
 
-// stage 1: grid (nchunks, B), 1024 threads: processors + per-chunk top-64
-__global__ void __launch_bounds__(1024) topk_stage1_kernel(const SamplerParams p) {
-  __shared__ Cand a[kTopChunk];
+// order-preserving float -> uint key (larger float <=> larger key; -inf is the smallest finite key)
+NT_DEVINL uint32_t f2key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Block-wide radix select (4 passes of 8 bits, MSB first) over n keys in shared memory:
+// finds the key of the k-th largest element and how many elements equal to it belong to the
+// top-k.  All kSelThreads threads of the block must call it.  scratch: >= 258 uint32.
+NT_DEVINL void radix_select_kth(const uint32_t* keys, int n, int k, uint32_t* scratch, uint32_t& thr, int& take_eq) {
+  uint32_t* hist = scratch;           // [256]
+  uint32_t* sel = scratch + 256;      // [2]: bin, remaining
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t prefix = 0, mask = 0;
+  int remaining = k;
+  const int n_pad = (n + 31) & ~31;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 256; i += kSelThreads) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n_pad; i += kSelThreads) {
+      uint32_t bin = 0xffffffffu;
+      if (i < n) {
+        const uint32_t key = keys[i];
+        if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+      }
+      // one shared-memory atomic per distinct bin per warp (logits crowd into few top-byte bins)
+      const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+      if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+    }
+    __syncthreads();
+    if (tid < 32) {
+      uint32_t c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c[j] = hist[8 * lane + j];
+        sum += c[j];
+      }
+      uint32_t suf = sum;  // elements in bins >= 8*lane
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, suf, off);
+        if (lane + off < 32) suf += t;
+      }
+      const uint32_t above = suf - sum;
+      if (above < static_cast<uint32_t>(remaining) && static_cast<uint32_t>(remaining) <= suf) {
+        uint32_t acc = above;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+          if (acc + c[j] >= static_cast<uint32_t>(remaining)) {
+            sel[0] = 8 * lane + j;
+            sel[1] = remaining - acc;
+            break;
+          }
+          acc += c[j];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= sel[0] << shift;
+    mask |= 0xffu << shift;
+    remaining = static_cast<int>(sel[1]);
+    __syncthreads();
+  }
+  thr = prefix;
+  take_eq = remaining;
+}
+
+// Deterministic compaction of the top-k winners (keys > thr, plus the first take_eq keys == thr
+// in index order) into out slots [0, k).  Elements are owned in contiguous runs per thread so a
+// block scan preserves index order.  scratch: >= 2*8+2 uint32.
+template <typename Emit>
+NT_DEVINL void compact_topk(const uint32_t* keys, int n, uint32_t thr, int take_eq, uint32_t* scratch, Emit emit) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + kSelThreads - 1) / kSelThreads;
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  int ngt = 0, neq = 0;
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t key = keys[i];
+    ngt += key > thr;
+    neq += key == thr;
+  }
+  // exclusive scans across the block (warp shuffles + one smem hop)
+  int sgt = ngt, seq = neq;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, sgt, off), b = __shfl_up_sync(0xffffffffu, seq, off);
+    if (lane >= off) sgt += a, seq += b;
+  }
+  uint32_t* wg = scratch;       // [8] per-warp totals (gt)
+  uint32_t* we = scratch + 8;   // [8] per-warp totals (eq)
+  __syncthreads();
+  if (lane == 31) wg[warp] = sgt, we[warp] = seq;
+  __syncthreads();
+  int bg = 0, be = 0, total_gt = 0;
+  for (int w = 0; w < kSelThreads / 32; ++w) {
+    if (w < warp) bg += wg[w], be += we[w];
+    total_gt += wg[w];
+  }
+  int pos_gt = bg + sgt - ngt;          // exclusive prefix of "greater" elements
+  int idx_eq = be + seq - neq;          // exclusive prefix of "equal" elements
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t key = keys[i];
+    if (key > thr) {
+      emit(pos_gt++, i);
+    } else if (key == thr) {
+      if (idx_eq < take_eq) emit(total_gt + idx_eq, i);
+      ++idx_eq;
+    }
+  }
+}
+
+// stage 1: grid (nchunks, B), 256 threads: logits processors + exact top-64 of a 2048-logit chunk
+__global__ void __launch_bounds__(kSelThreads) topk_stage1_kernel(const SamplerParams p) {
+  __shared__ uint32_t keys[kTopChunk];
+  __shared__ uint32_t scratch[260];
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.y, chunk = blockIdx.x, tid = threadIdx.x;
@@ -511,86 +626,95 @@ __global__ void __launch_bounds__(1024) topk_stage1_kernel(const SamplerParams p
   const bool mask_eos = ngen < p.sp.min_new_tokens;
   const float inv_t = 1.0f / p.sp.temperature;
   const float* lg = p.logits + static_cast<long long>(b) * p.V;
-  for (int e = tid; e < kTopChunk; e += 1024) {
-    const int idx = chunk * kTopChunk + e;
-    Cand c;
-    if (idx < p.V) {
-      float v = lg[idx];
-      if (mask_eos && idx == p.sp.eos_id) v = -INFINITY;  // MinNewTokensLength
-      c.v = v * inv_t;                                    // Temperature
-      c.i = idx;
-    } else {
-      c.v = -INFINITY;
-      c.i = 0x7fffffff;
-    }
-    a[e] = c;
+  const int base = chunk * kTopChunk;
+  const int n = min(kTopChunk, p.V - base);
+  for (int e = tid; e < n; e += kSelThreads) {
+    float v = lg[base + e];
+    if (mask_eos && base + e == p.sp.eos_id) v = -INFINITY;  // MinNewTokensLength
+    keys[e] = f2key(v * inv_t);                              // Temperature
   }
   __syncthreads();
-  bitonic_sort_desc(a, kTopChunk, tid, 1024);
-  if (tid < kTopKeep) {
-    const long long o = (static_cast<long long>(b) * p.nchunks + chunk) * kTopKeep + tid;
-    p.cand_val[o] = a[tid].v;
-    p.cand_idx[o] = a[tid].i;
+  const long long o = (static_cast<long long>(b) * p.nchunks + chunk) * kTopKeep;
+  const int k = min(kTopKeep, n);
+  uint32_t thr;
+  int take_eq;
+  radix_select_kth(keys, n, k, scratch, thr, take_eq);
+  compact_topk(keys, n, thr, take_eq, scratch, [&](int slot, int i) {
+    p.cand_val[o + slot] = lg[base + i];   // raw logit; stage 2 re-applies the processors
+    p.cand_idx[o + slot] = base + i;
+  });
+  for (int s = k + tid; s < kTopKeep; s += kSelThreads) {
+    p.cand_val[o + s] = -INFINITY;
+    p.cand_idx[o + s] = 0x7fffffff;
   }
 }
 
-// stage 2: grid (B), 1024 threads: merge candidates, softmax over top-k, draw, update state,
-// write the next step's embedding row.
-__global__ void __launch_bounds__(1024) topk_stage2_kernel(const SamplerParams p, const int n2) {
+// stage 2: grid (B), 256 threads: top-k of the candidates, softmax, draw, state update, next embedding
+__global__ void __launch_bounds__(kSelThreads) topk_stage2_kernel(const SamplerParams p, const int ncand) {
   extern __shared__ uint8_t smem_raw[];
-  Cand* a = reinterpret_cast<Cand*>(smem_raw);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(smem_raw);    // [ncand]
+  __shared__ uint32_t scratch[260];
+  __shared__ Cand win[kTopKeep];
   __shared__ int s_tok;
   pdl_launch_dependents();
   pdl_wait();
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int ncand = p.nchunks * kTopKeep;
-  for (int e = tid; e < n2; e += 1024) {
-    Cand c;
-    if (e < ncand) {
-      c.v = p.cand_val[static_cast<long long>(b) * ncand + e];
-      c.i = p.cand_idx[static_cast<long long>(b) * ncand + e];
-    } else {
-      c.v = -INFINITY;
-      c.i = 0x7fffffff;
-    }
-    a[e] = c;
-  }
-  __syncthreads();
-  bitonic_sort_desc(a, n2, tid, 1024);
-
   const bool stateless = p.n_generated_override != nullptr;
   const int ngen = stateless ? p.n_generated_override[b] : p.n_generated[b];
   const bool is_done = stateless ? false : (p.done[b] != 0);
-  const int k = min(p.sp.top_k, kTopKeep);
+  const bool mask_eos = ngen < p.sp.min_new_tokens;
+  const float inv_t = 1.0f / p.sp.temperature;
+  const float* cv = p.cand_val + static_cast<long long>(b) * ncand;
+  const int32_t* ci = p.cand_idx + static_cast<long long>(b) * ncand;
+  for (int e = tid; e < ncand; e += kSelThreads) {
+    float v = cv[e];
+    if (mask_eos && ci[e] == p.sp.eos_id) v = -INFINITY;
+    keys[e] = f2key(v * inv_t);
+  }
+  if (tid < kTopKeep) win[tid].v = -INFINITY, win[tid].i = 0x7fffffff;
+  __syncthreads();
+  const int k = min(min(p.sp.top_k, kTopKeep), ncand);
+  uint32_t thr;
+  int take_eq;
+  radix_select_kth(keys, ncand, k, scratch, thr, take_eq);
+  compact_topk(keys, ncand, thr, take_eq, scratch, [&](int slot, int i) {
+    float v = cv[i];
+    if (mask_eos && ci[i] == p.sp.eos_id) v = -INFINITY;
+    win[slot].v = v * inv_t;
+    win[slot].i = ci[i];
+  });
+  __syncthreads();
+  bitonic_sort_desc(win, kTopKeep, tid, kSelThreads);   // 64 winners: (score desc, index asc)
+
   if (tid < 32) {
     // softmax over the k kept scores (TopK processor + softmax, utils.py:2789)
-    const float m = a[0].v;
-    const float e0 = (tid < k) ? __expf(a[tid].v - m) : 0.f;
-    const float e1 = (tid + 32 < k) ? __expf(a[tid + 32].v - m) : 0.f;
+    const float m = win[0].v;
+    const float e0 = (tid < k) ? __expf(win[tid].v - m) : 0.f;
+    const float e1 = (tid + 32 < k) ? __expf(win[tid + 32].v - m) : 0.f;
     const float sum = warp_sum(e0 + e1);
     if (p.dbg_topk_val) {
       p.dbg_topk_val[b * kTopKeep + tid] = (tid < k) ? e0 / sum : 0.f;
       p.dbg_topk_val[b * kTopKeep + tid + 32] = (tid + 32 < k) ? e1 / sum : 0.f;
-      p.dbg_topk_idx[b * kTopKeep + tid] = (tid < k) ? a[tid].i : -1;
-      p.dbg_topk_idx[b * kTopKeep + tid + 32] = (tid + 32 < k) ? a[tid + 32].i : -1;
+      p.dbg_topk_idx[b * kTopKeep + tid] = (tid < k) ? win[tid].i : -1;
+      p.dbg_topk_idx[b * kTopKeep + tid + 32] = (tid + 32 < k) ? win[tid + 32].i : -1;
     }
     if (tid == 0) {
       int tok;
       if (p.sp.forced && !stateless) {
         tok = p.sp.forced[static_cast<long long>(b) * p.max_new + ngen];
       } else if (p.sp.greedy) {
-        tok = a[0].i;
+        tok = win[0].i;
       } else {
         uint32_t ctr[4] = {static_cast<uint32_t>(stateless ? p.step_override : ngen), static_cast<uint32_t>(b), 0u, 0u};
         philox4x32_10(ctr, static_cast<uint32_t>(p.sp.seed), static_cast<uint32_t>(p.sp.seed >> 32));
         const float u = (ctr[0] >> 8) * (1.0f / 16777216.0f);  // [0,1)
         const float target = u * sum;
         float cum = 0.f;
-        tok = a[k - 1].i;
+        tok = win[k - 1].i;
         for (int j = 0; j < k; ++j) {
-          cum += __expf(a[j].v - m);
+          cum += __expf(win[j].v - m);
           if (cum > target) {
-            tok = a[j].i;
+            tok = win[j].i;
             break;
           }
         }
@@ -613,7 +737,7 @@ __global__ void __launch_bounds__(1024) topk_stage2_kernel(const SamplerParams p
   if (!stateless && !is_done && p.h) {
     const int tok = s_tok;
     const __nv_bfloat16* e = p.embed + static_cast<long long>(tok) * p.hidden;
-    for (int i = tid; i < p.hidden; i += 1024) p.h[static_cast<long long>(b) * p.hidden + i] = __bfloat162float(e[i]);
+    for (int i = tid; i < p.hidden; i += kSelThreads) p.h[static_cast<long long>(b) * p.hidden + i] = __bfloat162float(e[i]);
   }
 }
 
@@ -621,18 +745,16 @@ int launch_sampler(const SamplerParams& p, int B, cudaStream_t stream) {
   if (p.sp.top_k < 1 || p.sp.top_k > kTopKeep) return set_error(NT_ERR_INVALID, "sampler: top_k=%d not in 1..64", p.sp.top_k);
   if (!(p.sp.temperature > 0.f)) return set_error(NT_ERR_INVALID, "sampler: temperature must be > 0");
   const int ncand = p.nchunks * kTopKeep;
-  int n2 = 64;
-  while (n2 < ncand) n2 <<= 1;
-  if (n2 > 16384) return set_error(NT_ERR_INVALID, "sampler: vocabulary too large (%d)", p.V);
-  int rc = launch_kernel(topk_stage1_kernel, dim3(p.nchunks, B), dim3(1024), 0, stream, true, p);
+  const size_t smem = size_t(ncand) * sizeof(uint32_t);
+  if (smem > 200 * 1024) return set_error(NT_ERR_INVALID, "sampler: vocabulary too large (%d)", p.V);
+  int rc = launch_kernel(topk_stage1_kernel, dim3(p.nchunks, B), dim3(kSelThreads), 0, stream, true, p);
   if (rc) return rc;
-  const size_t smem = size_t(n2) * sizeof(Cand);
   static size_t attr = 0;
-  if (smem > 48 * 1024 && attr < smem) {
+  if (smem > 40 * 1024 && attr < smem) {
     NT_CUDA_CHECK(cudaFuncSetAttribute(topk_stage2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     attr = smem;
   }
-  return launch_kernel(topk_stage2_kernel, dim3(B), dim3(1024), smem, stream, true, p, n2);
+  return launch_kernel(topk_stage2_kernel, dim3(B), dim3(kSelThreads), smem, stream, true, p, ncand);
 }
 
 // =================================================================================== prefill helpers

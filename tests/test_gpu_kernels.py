@@ -132,7 +132,8 @@ def test_rmsnorm_rows(cuda):
     w = 1 + 0.1 * torch.randn(896, generator=g)
     xo = torch.empty(37, 896, device=cuda)
     xb = torch.empty(37, 896, dtype=torch.bfloat16, device=cuda)
-    _lib.check(L.nt_op_rmsnorm(x.to(cuda).data_ptr(), w.to(cuda).data_ptr(), 1e-6, 37, 896, xo.data_ptr(), xb.data_ptr(),
+    xd, wd = x.to(cuda), w.to(cuda)          # keep the device copies alive across the call
+    _lib.check(L.nt_op_rmsnorm(xd.data_ptr(), wd.data_ptr(), 1e-6, 37, 896, xo.data_ptr(), xb.data_ptr(),
                                _lib.current_stream_ptr()))
     torch.cuda.synchronize()
     ref = rms_norm(x, w, 1e-6)

@@ -1,0 +1,267 @@
+"""CPU: host-side logic above the C-ABI — prompt construction, code<->token mapping, streaming
+cross-fade, KV page pool, weight packing, checkpoint reading, sharding plan.  A fake tokenizer /
+phonemizer stands in for the HF tokenizer and espeak (neither is available offline)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import stream_oracle as SO
+
+
+class FakeTokenizer:
+    """Character-level tokenizer with the special tokens the reference adds (TRAINING.md:33-57)."""
+    SPECIALS = ["<|TEXT_REPLACE|>", "<|TEXT_PROMPT_START|>", "<|TEXT_PROMPT_END|>", "<|SPEECH_REPLACE|>",
+                "<|SPEECH_GENERATION_START|>", "<|SPEECH_GENERATION_END|>"]
+
+    def __init__(self, n_speech=65536):
+        self.chars = {chr(c): c for c in range(32, 1024)}
+        self.chars["\n"] = 10
+        self.special_base = 2000
+        self.speech_base = 3000
+        self.n_speech = n_speech
+
+    def convert_tokens_to_ids(self, tok):
+        if tok in self.SPECIALS:
+            return self.special_base + self.SPECIALS.index(tok)
+        if tok.startswith("<|speech_"):
+            return self.speech_base + int(tok[9:-2])
+        raise KeyError(tok)
+
+    def encode(self, text, add_special_tokens=True):
+        import re
+
+        out = []
+        for part in re.split(r"(<\|[A-Za-z_0-9]+\|>)", text):
+            if not part:
+                continue
+            if part.startswith("<|") and part.endswith("|>"):
+                out.append(self.convert_tokens_to_ids(part))
+            else:
+                out += [self.chars[c] for c in part]
+        return out
+
+    def decode(self, ids, add_special_tokens=False):
+        inv = {v: k for k, v in self.chars.items()}
+        s = ""
+        for i in ids:
+            if i >= self.speech_base:
+                s += f"<|speech_{i - self.speech_base}|>"
+            elif i >= self.special_base:
+                s += self.SPECIALS[i - self.special_base]
+            else:
+                s += inv[i]
+        return s
+
+
+class FakePhonemizer:
+    def phonemize(self, texts):
+        return [t.lower().replace(",", " ,") for t in texts]
+
+
+class FakeCodec:
+    device = torch.device("cpu")
+    max_batch = 4
+
+    def decode_code(self, codes):
+        return torch.zeros(codes.shape[0], 1, 480 * codes.shape[2]) + codes[:, :, :1].float() / 65536.0
+
+
+class FakeBackbone:
+    """transformers-style .generate(): appends fixed ids (some non-speech) and EOS."""
+    device = torch.device("cpu")
+
+    def __init__(self, tail):
+        self.tail = tail
+
+    def generate(self, ids, **kw):
+        self.kw = kw
+        return torch.cat((ids, torch.tensor([self.tail])), dim=1)
+
+
+def _tts(tail=None):
+    from neutts import NeuTTS
+
+    tok = FakeTokenizer()
+    tail = tail if tail is not None else [tok.speech_base + 5, 65, tok.speech_base + 70000, tok.speech_base + 9, tok.special_base + 5]
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return NeuTTS(tokenizer=tok, phonemizer=FakePhonemizer(), backbone=FakeBackbone(tail), codec=FakeCodec()), tok
+
+
+def _reference_template(tok, phon, ref_codes, ref_text, input_text):
+    """Restatement of neutts/neutts.py:303-332 (the id sequence the facade must reproduce)."""
+    to_ph = lambda t: " ".join(phon.phonemize([t])[0].split())
+    text = to_ph(ref_text) + " " + to_ph(input_text)
+    input_ids = tok.encode(text, add_special_tokens=False)
+    ids = tok.encode("user: Convert the text to speech:<|TEXT_REPLACE|>\nassistant:<|SPEECH_REPLACE|>")
+    i = ids.index(tok.convert_tokens_to_ids("<|TEXT_REPLACE|>"))
+    ids = ids[:i] + [tok.convert_tokens_to_ids("<|TEXT_PROMPT_START|>")] + input_ids + [tok.convert_tokens_to_ids("<|TEXT_PROMPT_END|>")] + ids[i + 1:]
+    j = ids.index(tok.convert_tokens_to_ids("<|SPEECH_REPLACE|>"))
+    codes = tok.encode("".join(f"<|speech_{c}|>" for c in ref_codes), add_special_tokens=False)
+    return ids[:j] + [tok.convert_tokens_to_ids("<|SPEECH_GENERATION_START|>")] + codes
+
+
+def test_facade_attributes_and_prompt_template():
+    tts, tok = _tts()
+    assert (tts.sample_rate, tts.max_context, tts.hop_length) == (24000, 2048, 480)
+    assert (tts.streaming_overlap_frames, tts.streaming_frames_per_chunk, tts.streaming_lookforward, tts.streaming_lookback,
+            tts.streaming_stride_samples) == (1, 25, 5, 50, 12000)
+    assert tts._is_quantized_model is False and tts._is_onnx_codec is False
+    ref = torch.tensor([5, 17, 65535, 0], dtype=torch.int32)
+    for codes in (ref, ref.numpy(), ref.tolist()):
+        got = tts._apply_chat_template(codes, "Hello, there", "General  Kenobi")
+        assert got == _reference_template(tok, tts.phonemizer, ref.tolist(), "Hello, there", "General  Kenobi")
+
+
+def test_facade_infer_drops_non_speech_tokens_and_returns_pcm():
+    tts, tok = _tts()
+    wav = tts.infer("Testing.", torch.tensor([1, 2, 3]), "ref text")
+    # the reference's own assertions (tests/test_neutts.py:55-58)
+    assert isinstance(wav, np.ndarray) and len(wav) > 0 and not np.isnan(wav).any() and wav.dtype in (np.float32, np.float64)
+    assert len(wav) == 480 * 2                   # 65 (text), speech_70000 (out of range) and EOS were dropped
+    assert tts.backbone.kw["max_length"] == 2048 and tts.backbone.kw["top_k"] == 50 and tts.backbone.kw["min_new_tokens"] == 50
+    assert tts.backbone.kw["temperature"] == 1.0 and tts.backbone.kw["do_sample"] is True
+    # string protocol of the seams
+    s = tts._infer_torch(tts._apply_chat_template([1], "a", "b"))
+    assert s.startswith("<|speech_5|>A<|speech_70000|><|speech_9|>")
+    assert len(tts._decode("<|speech_12|>junk<|speech_7|>")) == 960
+    with pytest.raises(ValueError, match="No valid speech tokens"):
+        tts._decode("no codes here")
+    tts2, tok2 = _tts(tail=[65, 66, tok.special_base + 5])
+    with pytest.raises(ValueError, match="No valid speech tokens"):
+        tts2.infer("x", [1], "y")
+
+
+def test_facade_rejects_unsupported_backends():
+    from neutts import NeuTTS
+    from neuttsair import NeuTTSAir
+
+    assert issubclass(NeuTTSAir, NeuTTS)
+    kw = dict(tokenizer=FakeTokenizer(), phonemizer=FakePhonemizer())
+    with pytest.raises(ValueError, match="GGUF"):
+        NeuTTS(backbone_repo="neuphonic/neutts-air-q4-gguf", codec=FakeCodec(), **kw)
+    with pytest.raises(ValueError, match="CUDA only"):
+        NeuTTS(backbone_repo="neuphonic/neutts-air", backbone_device="cpu", codec=FakeCodec(), **kw)
+    with pytest.raises(ValueError, match="Invalid codec repo"):
+        NeuTTS(backbone=FakeBackbone([1]), codec_repo="someone/else", **kw)
+    with pytest.raises(ValueError, match="ONNX"):
+        NeuTTS(backbone=FakeBackbone([1]), codec_repo="neuphonic/neucodec-onnx-decoder", **kw)
+
+
+def test_crossfade_equals_reference_overlap_add():
+    from neutts.neutts import _CrossFade
+
+    rng = np.random.default_rng(0)
+    frames = [rng.standard_normal(12960).astype(np.float32) for _ in range(5)] + [rng.standard_normal(7000).astype(np.float32)]
+    fade, out = _CrossFade(12000), []
+    for i, f in enumerate(frames):
+        out.append(fade.push(f, final=(i == len(frames) - 1)))
+    assert [len(o) for o in out[:-1]] == [12000] * 5
+    got = np.concatenate(out)
+    want = SO.linear_overlap_add(frames, 12000)
+    assert got.shape == want.shape and np.abs(got - want).max() < 1e-6
+
+
+def test_page_pool_and_weight_packing():
+    from neutts_air_b200.lm import LMShape, PagePool, _rope_pair_perm, pack_weights
+    from oracle import lm_oracle as LO
+    from tests.helpers import lm_state_dict
+
+    pool = PagePool(8, shuffle_seed=1)
+    a = pool.alloc(3)
+    b = pool.alloc(5)
+    assert sorted(a + b) == list(range(8))
+    with pytest.raises(RuntimeError):
+        pool.alloc(1)
+    pool.release(a)
+    assert sorted(pool.alloc(3)) == sorted(a)
+    assert _rope_pair_perm(2)[:6].tolist() == [0, 32, 1, 33, 2, 34] and _rope_pair_perm(2)[64:68].tolist() == [64, 96, 65, 97]
+    cfg = LO.LMConfig.tiny()
+    w = LO.random_weights(cfg, 0)
+    shape = LMShape(cfg.vocab_size, cfg.hidden_size, cfg.intermediate_size, cfg.num_layers, cfg.num_heads, cfg.num_kv_heads)
+    pk = pack_weights(shape, lm_state_dict(w), "cpu")
+    L0 = w.layers[0]
+    assert pk["wqkv"][0].shape == ((cfg.num_heads + 2 * cfg.num_kv_heads) * 64, cfg.hidden_size)
+    assert torch.equal(pk["wqkv"][0][1].float(), L0["wq"][32].bfloat16().float())              # partner row adjacent
+    assert torch.equal(pk["wqkv"][0][cfg.num_heads * 64 + 2].float(), L0["wk"][1].bfloat16().float())
+    assert torch.equal(pk["wqkv"][0][-1].float(), L0["wv"][-1].bfloat16().float())              # v rows keep natural order
+    assert torch.equal(pk["bqkv"][0][:4], torch.stack((L0["bq"][0], L0["bq"][32], L0["bq"][1], L0["bq"][33])))
+    assert torch.equal(pk["wgu"][0][0].float(), L0["wg"][0].bfloat16().float()) and torch.equal(pk["wgu"][0][1].float(), L0["wu"][0].bfloat16().float())
+    assert pk["lm_head"] is pk["embed"]
+
+
+def test_loader_reads_hf_checkpoint(tmp_path):
+    pytest.importorskip("transformers")
+    from neutts_air_b200 import loader
+    from neutts_air_b200.lm import LMShape
+    from oracle import lm_oracle as LO
+
+    cfg = LO.LMConfig.tiny()
+    w = LO.random_weights(cfg, 2)
+    LO.to_hf_model(cfg, w).save_pretrained(tmp_path)
+    hf_cfg = json.loads((tmp_path / "config.json").read_text())
+    shape = LMShape.from_hf_config(hf_cfg)
+    assert (shape.vocab_size, shape.hidden_size, shape.num_layers, shape.num_heads, shape.num_kv_heads, shape.head_dim) == \
+        (cfg.vocab_size, cfg.hidden_size, cfg.num_layers, cfg.num_heads, cfg.num_kv_heads, 64)
+    assert shape.rope_theta == 1e6 and shape.tie_embeddings
+    sd = loader.read_state_dict(loader.resolve_repo(str(tmp_path)))
+    assert torch.equal(sd["model.layers.1.mlp.down_proj.weight"], w.layers[1]["wd"])
+    with pytest.raises(FileNotFoundError):
+        loader.resolve_repo("definitely/not-a-repo-xyz")
+
+
+def test_codec_loader_key_mapping_and_packing():
+    from neutts_air_b200 import loader
+    from neutts_air_b200.codec import CodecShape, idft_basis, pack_weights
+    from oracle import codec_oracle as CO
+
+    cfg = CO.CodecConfig.tiny()
+    w = CO.random_weights(cfg, 1)
+    sd = {"generator.quantizer.project_out.weight": w.project_out_w, "generator.quantizer.project_out.bias": w.project_out_b,
+          "fc_post_a.weight": w.fc_post_a_w, "fc_post_a.bias": w.fc_post_a_b,
+          "generator.backbone.embed.weight": w.embed_w, "generator.backbone.embed.bias": w.embed_b,
+          "generator.backbone.final_layer_norm.weight": w.final_ln_w, "generator.backbone.final_layer_norm.bias": w.final_ln_b,
+          "generator.head.out.weight": w.head_w, "generator.head.out.bias": w.head_b}
+    names = dict(n1w="norm1.weight", n1b="norm1.bias", c1w="conv1.weight", c1b="conv1.bias", n2w="norm2.weight", n2b="norm2.bias",
+                 c2w="conv2.weight", c2b="conv2.bias")
+    for grp, blocks in (("prior_net", w.prior), ("post_net", w.post)):
+        for i, r in enumerate(blocks):
+            for k, v in r.items():
+                sd[f"generator.backbone.{grp}.{i}.{names[k]}"] = v
+    for i, b in enumerate(w.blocks):
+        p = f"generator.backbone.transformers.{i}."
+        sd.update({p + "att_norm.weight": b["att_norm"], p + "att.c_attn.weight": b["wqkv"], p + "att.c_proj.weight": b["wproj"],
+                   p + "ffn_norm.weight": b["ffn_norm"], p + "mlp.fc1.weight": b["fc1"], p + "mlp.fc2.weight": b["fc2"]})
+    shape, wd = loader.codec_weights_from_state_dict(sd)
+    assert (shape.hidden, shape.depth, shape.heads, shape.n_fft, shape.hop, shape.quant_dim) == (128, 2, 2, 64, 16, 64)
+    pk = pack_weights(shape, wd, "cpu")
+    # collapsed FSQ affine == fc_post_a(project_out(z)) on every digit vector
+    z = CO.fsq_dequant(torch.arange(0, 65536, 257), cfg)
+    want = (z @ w.project_out_w.T + w.project_out_b) @ w.fc_post_a_w.T + w.fc_post_a_b
+    assert float((z @ pk["fsq_w"].T + pk["fsq_b"] - want).abs().max()) < 1e-5
+    # tap-major conv flattening
+    assert torch.equal(pk["embed_w"][3, 2 * 128 + 5], w.embed_w[3, 5, 2])
+    # windowed inverse-rDFT basis reproduces irfft * hann
+    g = torch.Generator().manual_seed(0)
+    nb = 33
+    spec = torch.complex(torch.randn(4, nb, generator=g), torch.randn(4, nb, generator=g))
+    B = idft_basis(64, 96)
+    got = torch.cat((spec.real, spec.imag), 1) @ B[:, :2 * nb].T
+    ref = torch.fft.irfft(spec, 64, dim=1) * torch.hann_window(64)
+    assert float((got - ref).abs().max()) < 1e-5 and float(B[:, 2 * nb:].abs().max()) == 0.0
+
+
+def test_shard_plan_is_a_balanced_partition():
+    from neutts_air_b200 import dist
+
+    lens = [700, 210, 1400, 333, 900, 901, 250, 1111, 640]
+    for ws in (1, 2, 4, 8):
+        plan = dist.shard_plan(len(lens), lens, ws)
+        assert sorted(i for p in plan for i in p) == list(range(len(lens)))
+        assert max(len(p) for p in plan) - min(len(p) for p in plan) <= 1
+    loads = [sum(lens[i] for i in p) for p in dist.shard_plan(len(lens), lens, 2)]
+    assert max(loads) / min(loads) < 1.25
