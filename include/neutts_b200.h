@@ -161,6 +161,8 @@ int nt_lm_head_gemv(nt_lm* lm, const float* h, int B, float* logits, void* strea
  * internal activation buffer by name ("h", "q", "qkv", "attn", "act", "logits", "xn", "attn_bf16",
  * "act_bf16", "h_last"); the pointer lies inside the caller's workspace. */
 int nt_lm_debug_set_layers(nt_lm* lm, int n_layers);
+/* launch-latency probe: n dependent trivial kernels (grid x block) each incrementing *counter */
+int nt_debug_launch_chain(int n, int grid, int block, int* counter, void* stream);
 void* nt_lm_debug_ptr(nt_lm* lm, const char* name);
 
 /* ------------------------------------------------------------------------------------------

@@ -12,6 +12,7 @@ namespace nt {
 
 int set_error(int code, const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
+bool pdl_disabled();  // NT_NO_PDL=1: launch without the programmatic-dependent-launch attribute (experiments)
 
 #define NT_CUDA_CHECK(expr)                                                                          \
   do {                                                                                               \
@@ -34,7 +35,7 @@ int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, 
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = (pdl && !pdl_disabled()) ? 1 : 0;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
   if (e != cudaSuccess) return set_error(NT_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
   g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "lm_kernels.cuh"
+#include "lm_mega.cuh"
 
 namespace nt {
 
@@ -28,6 +29,17 @@ static bool env_flag(const char* name) {
   const char* v = getenv(name);
   return v && v[0] && v[0] != '0';
 }
+bool pdl_disabled() {
+  static const bool off = env_flag("NT_NO_PDL");
+  return off;
+}
+
+// launch-latency probe: a chain of dependent trivial kernels (profiles/probe_launch.py)
+__global__ void noop_chain_kernel(int* p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (p && threadIdx.x == 0 && blockIdx.x == 0) p[0] += 1;
+}
 
 }  // namespace nt
 
@@ -45,6 +57,10 @@ struct nt_lm {
   float *h, *q, *attn, *act, *logits, *part_o, *part_ml, *cand_val, *inv_freq, *qkv, *h_last;
   int *counters, *cand_idx, *tok_seq, *tok_pos, *cu_dev, *last_rows, *iota;
   __nv_bfloat16 *xn, *attn_bf16, *act_bf16;
+  // megakernel tables (device)
+  MegaPhase* phase_tab;
+  const float** ptr_tab;   // [3][n_layers]: ln1, bqkv, ln2
+  unsigned* gbar;
   // cached decode-step graph
   cudaGraphExec_t graph = nullptr;
   std::vector<uint8_t> graph_key;
@@ -89,6 +105,9 @@ static size_t lm_carve(const nt_lm_config& c, void* ws, size_t bytes, F&& assign
     (L)->xn = a.take<__nv_bfloat16>(size_t(rows) * H);                                         \
     (L)->attn_bf16 = a.take<__nv_bfloat16>(size_t(rows) * c.n_heads * 64);                     \
     (L)->act_bf16 = a.take<__nv_bfloat16>(size_t(rows) * I);                                   \
+    (L)->phase_tab = a.take<MegaPhase>(size_t(4) * c.n_layers + 1);                            \
+    (L)->ptr_tab = a.take<const float*>(size_t(3) * c.n_layers);                               \
+    (L)->gbar = a.take<unsigned>(64);                                                          \
   }
 
 static int lm_check_config(const nt_lm_config* c) {
@@ -166,6 +185,26 @@ extern "C" int nt_lm_create(const nt_lm_config* cfg, const nt_lm_weights* w, voi
       cudaMemset(lm->counters, 0, size_t(c.max_batch) * c.n_kv_heads * sizeof(int)) != cudaSuccess) {
     delete lm;
     return set_error(NT_ERR_CUDA, "workspace initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  {
+    std::vector<MegaPhase> ph(size_t(4) * c.n_layers + 1);
+    std::vector<const float*> pt(size_t(3) * c.n_layers);
+    const int HD = c.n_heads * 64;
+    for (int l = 0; l < c.n_layers; ++l) {
+      ph[4 * l + 0] = MegaPhase{lm->wqkv[l], lm->qkv_n, c.hidden};
+      ph[4 * l + 1] = MegaPhase{lm->wo[l], c.hidden, HD};
+      ph[4 * l + 2] = MegaPhase{lm->wgu[l], 2 * c.inter, c.hidden};
+      ph[4 * l + 3] = MegaPhase{lm->wd[l], c.hidden, c.inter};
+      pt[l] = lm->ln1[l];
+      pt[c.n_layers + l] = lm->bqkv[l];
+      pt[2 * c.n_layers + l] = lm->ln2[l];
+    }
+    ph[4 * c.n_layers] = MegaPhase{lm->lm_head, c.vocab_size, c.hidden};
+    if (cudaMemcpy(lm->phase_tab, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(lm->ptr_tab, pt.data(), pt.size() * sizeof(const float*), cudaMemcpyHostToDevice) != cudaSuccess) {
+      delete lm;
+      return set_error(NT_ERR_CUDA, "megakernel table upload failed");
+    }
   }
   if (cudaStreamCreateWithFlags(&lm->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete lm;
@@ -396,6 +435,30 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
   if (rc) return rc;
   if (n_steps < 0) return set_error(NT_ERR_INVALID, "negative step count");
 
+  if (n_steps == 0) return NT_OK;
+  if (B <= 4 && !env_flag("NT_NO_MEGA") && c.hidden % 64 == 0) {
+    // persistent megakernel: every layer, the lm_head, the sampler and all n_steps in one launch
+    MegaParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_layers = lm->debug_layers >= 0 ? lm->debug_layers : c.n_layers;
+    P.total_layers = c.n_layers;
+    P.hidden = c.hidden, P.inter = c.inter, P.n_heads = c.n_heads, P.qkv_n = lm->qkv_n, P.vocab = c.vocab_size;
+    P.eps = c.rms_eps, P.scale_log2 = (1.0f / 8.0f) * 1.4426950408889634f;
+    P.phases = lm->phase_tab;
+    P.ln1 = lm->ptr_tab, P.bqkv = lm->ptr_tab + c.n_layers, P.ln2 = lm->ptr_tab + 2 * c.n_layers;
+    P.final_norm = lm->final_norm, P.inv_freq = lm->inv_freq;
+    P.h = lm->h, P.q = lm->q, P.attn = lm->attn, P.act = lm->act, P.logits = lm->logits;
+    P.kv = make_kv(lm, st);
+    P.part_o = lm->part_o, P.part_ml = lm->part_ml, P.counters = lm->counters, P.max_splits = lm->max_splits;
+    P.samp = make_sampler(lm, st, sp);
+    P.samp.advance = 1;
+    P.gbar = lm->gbar;
+    P.n_steps = n_steps;
+    P.logits_out = logits_out;
+    if ((rc = launch_sampler_check(P.samp))) return rc;
+    return launch_decode_mega(P, B, lm->num_sms, stream);
+  }
+
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   NT_CUDA_CHECK(cudaStreamIsCapturing(stream, &cap));
   const bool use_graph = !logits_out && cap == cudaStreamCaptureStatusNone && !env_flag("NT_NO_GRAPH") && n_steps > 1;
@@ -464,6 +527,14 @@ extern "C" void* nt_lm_debug_ptr(nt_lm* lm, const char* name) {
   for (const auto& e : tab)
     if (!strcmp(e.n, name)) return e.p;
   return nullptr;
+}
+
+extern "C" int nt_debug_launch_chain(int n, int grid, int block, int* counter, void* stream) {
+  for (int i = 0; i < n; ++i) {
+    int rc = launch_kernel(noop_chain_kernel, dim3(grid), dim3(block), 0, reinterpret_cast<cudaStream_t>(stream), true, counter);
+    if (rc) return rc;
+  }
+  return NT_OK;
 }
 
 extern "C" int nt_lm_head_gemv(nt_lm* lm, const float* h, int B, float* logits, void* stream) {

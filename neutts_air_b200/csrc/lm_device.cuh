@@ -1,0 +1,617 @@
+// Device-side building blocks of the decode path, shared by the per-op kernels (lm_kernels.cu)
+// and the persistent decode megakernel (lm_mega.cu).  Every block-cooperative function takes a
+// `Sync` functor: SyncAll (= __syncthreads, per-op kernels) or SyncConsumers (named barrier
+// over the 256 consumer threads of the megakernel, whose producer warp never joins).
+// All functions assume the cooperating threads are threadIdx.x in [0, 256).
+#pragma once
+#include "lm_kernels.cuh"
+
+namespace nt {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+
+struct SyncAll {
+  NT_DEVINL void operator()() const { __syncthreads(); }
+};
+struct SyncConsumers {
+  NT_DEVINL void operator()() const { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+};
+
+// mutable cross-CTA state is always read through L2 (L1 is not coherent across SMs)
+template <typename T>
+NT_DEVINL T ld_cg(const T* p) {
+  return __ldcg(p);
+}
+
+// =================================================================================== GEMV pieces
+// x planes: element k = 8c + j of batch row b lives in xs[(2b + j/4) * nch + c] component j%4, so
+// the two float4 reads that pair with one 16-byte bf16 weight chunk are conflict-free.
+template <int NB, typename Sync>
+NT_DEVINL void load_x_planes(const float* x, long long ldx, int K, const float* norm_w, float eps, float4* xs,
+                             float* s_part /*[8][4]*/, float* s_scale /*[4]*/, Sync sync) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nch = K >> 3, nvec = K >> 2;
+  float ssq[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) ssq[b] = 0.f;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const float4* src = reinterpret_cast<const float4*>(x + b * ldx);
+    for (int m = tid; m < nvec; m += kConsumerThreads) {
+      const float4 v = __ldcg(src + m);
+      xs[(2 * b + (m & 1)) * nch + (m >> 1)] = v;
+      ssq[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+  }
+  if (norm_w) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const float t = warp_sum(ssq[b]);
+      if (lane == 0) s_part[warp * 4 + b] = t;
+    }
+  }
+  sync();
+  if (norm_w) {
+    if (tid < NB) {
+      float t = 0.f;
+      for (int w = 0; w < kConsumerWarps; ++w) t += s_part[w * 4 + tid];
+      s_scale[tid] = rsqrtf(t / static_cast<float>(K) + eps);
+    }
+    sync();
+    const float4* nw = reinterpret_cast<const float4*>(norm_w);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const float sc = s_scale[b];
+      for (int m = tid; m < nvec; m += kConsumerThreads) {
+        float4& v = xs[(2 * b + (m & 1)) * nch + (m >> 1)];
+        const float4 g = __ldg(nw + m);
+        v.x = v.x * sc * g.x, v.y = v.y * sc * g.y, v.z = v.z * sc * g.z, v.w = v.w * sc * g.w;
+      }
+    }
+    sync();
+  }
+}
+
+// dot products of one unit (two adjacent bf16 rows in shared memory) with the NB x-vectors over
+// 16-byte chunks [c_lo, c_hi), strided by lane.  Partial sums stay per lane.
+template <int NB>
+NT_DEVINL void unit_dot(const uint4* r0, const uint4* r1, const float4* xs, int nch, int c_lo, int c_hi, int lane,
+                        float (&d0)[NB], float (&d1)[NB]) {
+  for (int c = c_lo + lane; c < c_hi; c += 32) {
+    float f0[8], f1[8];
+    bf16x8_to_f32(r0[c], f0);
+    bf16x8_to_f32(r1[c], f1);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      const float4 xa = xs[(2 * b) * nch + c];
+      const float4 xb = xs[(2 * b + 1) * nch + c];
+      d0[b] += f0[0] * xa.x + f0[1] * xa.y + f0[2] * xa.z + f0[3] * xa.w + f0[4] * xb.x + f0[5] * xb.y + f0[6] * xb.z +
+               f0[7] * xb.w;
+      d1[b] += f1[0] * xa.x + f1[1] * xa.y + f1[2] * xa.z + f1[3] * xa.w + f1[4] * xb.x + f1[5] * xb.y + f1[6] * xb.z +
+               f1[7] * xb.w;
+    }
+  }
+}
+
+// Epilogue of one unit (rows 2u, 2u+1).  All lanes hold the full sums; lane b finishes batch row b.
+template <int NB>
+NT_DEVINL void gemv_epilogue(const GemvParams& p, int u, float (&d0)[NB], float (&d1)[NB], int lane) {
+  if (lane >= NB) return;
+  const int b = lane;
+  float a0 = d0[0], a1 = d1[0];
+#pragma unroll
+  for (int i = 1; i < NB; ++i)
+    if (b == i) a0 = d0[i], a1 = d1[i];
+  const int r0 = 2 * u;
+  if (p.bias) {
+    a0 += __ldg(p.bias + r0);
+    a1 += __ldg(p.bias + r0 + 1);
+  }
+  if (p.epi == GEMV_STORE) {
+    if (p.residual) {
+      const float2 r = __ldcg(reinterpret_cast<const float2*>(p.residual + b * p.ldr + r0));
+      a0 += r.x;
+      a1 += r.y;
+    }
+    *reinterpret_cast<float2*>(p.out + b * p.ldo + r0) = make_float2(a0, a1);
+  } else if (p.epi == GEMV_SWIGLU) {
+    p.out[b * p.ldo + u] = silu(a0) * a1;
+  } else {  // GEMV_QKV_ROPE
+    const int head = u >> 5;  // 32 units per 64-row head
+    const int i = u & 31;
+    const int pos = __ldcg(p.kv.seq_lens + b);
+    const int n_kv = p.kv.n_kv_heads;
+    if (head < p.n_heads + n_kv) {
+      // rows (i, i+32) of a q/k head: half-split rotation (modeling_qwen2.py:116-146)
+      float s, c;
+      sincosf(static_cast<float>(pos) * __ldg(p.inv_freq + i), &s, &c);
+      const float lo = a0 * c - a1 * s;
+      const float hi = a1 * c + a0 * s;
+      if (head < p.n_heads) {
+        float* q = p.q_out + (static_cast<long long>(b) * p.n_heads + head) * 64;
+        q[i] = lo;
+        q[i + 32] = hi;
+      } else if (pos < p.kv.max_ctx) {
+        const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + (pos >> 6));
+        __nv_bfloat16* kp = p.kv.page_ptr(p.layer, 0, page, head - p.n_heads) + (pos & 63) * 64;
+        kp[i] = __float2bfloat16(lo);
+        kp[i + 32] = __float2bfloat16(hi);
+      }
+    } else if (pos < p.kv.max_ctx) {
+      const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + (pos >> 6));
+      __nv_bfloat16* vp = p.kv.page_ptr(p.layer, 1, page, head - p.n_heads - n_kv) + (pos & 63) * 64;
+      *reinterpret_cast<__nv_bfloat162*>(vp + 2 * i) = __floats2bfloat162_rn(a0, a1);
+    }
+  }
+}
+
+// One ring stage of a GEMV phase, executed by the 8 consumer warps.
+//   wpu == 1: the stage holds up to 8 units, warp w owns unit w;
+//   wpu == 8: the stage holds one unit, the warps split K and reduce through `red` (double-buffered
+//             by `parity`), warp 0 finishes.
+// `release` is called once per warp as soon as the warp has finished reading the stage.
+template <int NB, typename Release>
+NT_DEVINL void gemv_consume_stage(const GemvParams& p, const uint8_t* st, const float4* xs, float* red, int wpu,
+                                  int first_unit_local, int units_in_stage, int u_begin, int parity, Release release) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nch = p.K >> 3;
+  const int unit_bytes = 4 * p.K;
+  float d0[NB], d1[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) d0[b] = d1[b] = 0.f;
+  if (wpu == 1) {
+    const bool has = warp < units_in_stage;
+    if (has) {
+      const uint4* r0 = reinterpret_cast<const uint4*>(st + static_cast<size_t>(warp) * unit_bytes);
+      unit_dot<NB>(r0, r0 + nch, xs, nch, 0, nch, lane, d0, d1);
+    }
+    __syncwarp();
+    release();
+    if (has) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        d0[b] = warp_sum(d0[b]);
+        d1[b] = warp_sum(d1[b]);
+      }
+      gemv_epilogue<NB>(p, u_begin + first_unit_local + warp, d0, d1, lane);
+    }
+  } else {
+    const int c_lo = (nch * warp) / kConsumerWarps, c_hi = (nch * (warp + 1)) / kConsumerWarps;
+    const uint4* r0 = reinterpret_cast<const uint4*>(st);
+    unit_dot<NB>(r0, r0 + nch, xs, nch, c_lo, c_hi, lane, d0, d1);
+    __syncwarp();
+    release();
+    float* rbuf = red + parity * (kConsumerWarps * 2 * 4);
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      d0[b] = warp_sum(d0[b]);
+      d1[b] = warp_sum(d1[b]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        rbuf[(warp * 2 + 0) * 4 + b] = d0[b];
+        rbuf[(warp * 2 + 1) * 4 + b] = d1[b];
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 consumer warps (also the whole CTA minus the producer)
+    if (warp == 0) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        float t0 = 0.f, t1 = 0.f;
+        for (int w = 0; w < kConsumerWarps; ++w) {
+          t0 += rbuf[(w * 2 + 0) * 4 + b];
+          t1 += rbuf[(w * 2 + 1) * 4 + b];
+        }
+        d0[b] = t0, d1[b] = t1;
+      }
+      gemv_epilogue<NB>(p, u_begin + first_unit_local, d0, d1, lane);
+    }
+  }
+}
+
+// =================================================================================== decode attention
+struct AttnSmem {
+  __nv_bfloat16 k[64 * 64];
+  __nv_bfloat16 v[64 * 64];
+  float q[8][64];
+  float s[8][64];
+  float ml[8][2];
+  float red[4][8][64];
+};
+struct AttnSync {      // lives outside any aliased shared-memory region
+  uint64_t bar;        // mbarrier (count 1) completed by the K/V bulk copies
+  uint32_t uses;       // completed phases so far (parity bookkeeping across items)
+  int last;
+};
+
+// One (sequence b, kv head, split) work item: a 64-token page of K and V staged by bulk copies,
+// fp32 scores / softmax partials / P.V, then the last-arriving item of (b, kv head) merges the splits.
+// sy->bar must be initialised (count 1) and sy->uses must count its completed phases.
+template <typename Sync>
+NT_DEVINL void attn_decode_item(const AttnDecParams& p, int b, int kvh, int split, int n_ctx, int nsplit, AttnSmem* sm, AttnSync* sy,
+                                Sync sync) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_rep = p.n_rep;
+  const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + split);
+  const uint32_t parity = sy->uses & 1;
+  sync();  // previous item's readers are done with the staging buffers; `uses` was read by everyone
+  if (tid == 0) {
+    // K/V rows of this step were written through the generic proxy (possibly by another CTA, ordered by
+    // the grid barrier); the bulk copy reads through the async proxy
+    asm volatile("fence.proxy.async;" ::: "memory");
+    mbar_arrive_expect_tx(&sy->bar, 2 * 8192);
+    bulk_g2s(sm->k, p.kv.page_ptr(p.layer, 0, page, kvh), 8192, &sy->bar);
+    bulk_g2s(sm->v, p.kv.page_ptr(p.layer, 1, page, kvh), 8192, &sy->bar);
+    sy->uses += 1;
+  }
+  for (int i = tid; i < n_rep * 64; i += kConsumerThreads)
+    sm->q[i >> 6][i & 63] = __ldcg(p.q + (static_cast<long long>(b) * p.n_heads + kvh * n_rep + (i >> 6)) * 64 + (i & 63));
+  sync();
+  mbar_wait(&sy->bar, parity);
+
+  {  // scores: thread = (token, quarter of the head dim)
+    const int tok = tid >> 2, part = tid & 3;
+    const uint4* kr = reinterpret_cast<const uint4*>(sm->k + tok * 64 + part * 16);
+    float kf[16];
+    {
+      float t[8];
+      bf16x8_to_f32(kr[0], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kf[j] = t[j];
+      bf16x8_to_f32(kr[1], t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) kf[8 + j] = t[j];
+    }
+    const bool valid = (split * 64 + tok) < n_ctx;
+    for (int h = 0; h < n_rep; ++h) {
+      float d = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) d += kf[j] * sm->q[h][part * 16 + j];
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      if (part == 0) sm->s[h][tok] = valid ? d * p.scale_log2 : -INFINITY;
+    }
+  }
+  sync();
+  if (warp < n_rep) {  // per-head softmax partials (fp32, base-2 exponent with log2e folded into the scale)
+    const float s0 = sm->s[warp][lane], s1 = sm->s[warp][lane + 32];
+    const float m = warp_max(fmaxf(s0, s1));  // the first token of every live split is valid -> finite
+    const float p0 = exp2f(s0 - m), p1 = exp2f(s1 - m);
+    const float l = warp_sum(p0 + p1);
+    sm->s[warp][lane] = p0;
+    sm->s[warp][lane + 32] = p1;
+    if (lane == 0) sm->ml[warp][0] = m, sm->ml[warp][1] = l;
+  }
+  sync();
+  {  // P.V : thread = (dim, token group of 16)
+    const int d = tid & 63, g = tid >> 6;
+    float acc[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) acc[h] = 0.f;
+    for (int t = g * 16; t < g * 16 + 16; ++t) {
+      const float v = __bfloat162float(sm->v[t * 64 + d]);
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        if (h < n_rep) acc[h] += sm->s[h][t] * v;
+    }
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+      if (h < n_rep) sm->red[g][h][d] = acc[h];
+  }
+  sync();
+  for (int i = tid; i < n_rep * 64; i += kConsumerThreads) {
+    const int h = i >> 6, d = i & 63;
+    const float o = sm->red[0][h][d] + sm->red[1][h][d] + sm->red[2][h][d] + sm->red[3][h][d];
+    const long long hh = static_cast<long long>(b) * p.n_heads + kvh * n_rep + h;
+    p.part_o[(hh * p.max_splits + split) * 64 + d] = o;
+    if (d == 0) {
+      p.part_ml[(hh * p.max_splits + split) * 2 + 0] = sm->ml[h][0];
+      p.part_ml[(hh * p.max_splits + split) * 2 + 1] = sm->ml[h][1];
+    }
+  }
+  // last item of this (sequence, kv head) merges the splits in split order (deterministic)
+  __threadfence();
+  sync();
+  if (tid == 0) {
+    const int old = atomicAdd(&p.counters[b * p.kv.n_kv_heads + kvh], 1);
+    sy->last = (old == nsplit - 1);
+  }
+  sync();
+  if (!sy->last) return;
+  __threadfence();
+  for (int i = tid; i < n_rep * 64; i += kConsumerThreads) {
+    const int h = i >> 6, d = i & 63;
+    const long long hh = static_cast<long long>(b) * p.n_heads + kvh * n_rep + h;
+    float M = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(&p.part_ml[(hh * p.max_splits + s) * 2]));
+    float L = 0.f, O = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const float w = exp2f(__ldcg(&p.part_ml[(hh * p.max_splits + s) * 2]) - M);
+      L += w * __ldcg(&p.part_ml[(hh * p.max_splits + s) * 2 + 1]);
+      O += w * __ldcg(&p.part_o[(hh * p.max_splits + s) * 64 + d]);
+    }
+    p.out[hh * 64 + d] = O / L;
+    if (p.out_bf16) p.out_bf16[hh * 64 + d] = __float2bfloat16(O / L);
+  }
+  if (tid == 0) p.counters[b * p.kv.n_kv_heads + kvh] = 0;
+}
+
+// =================================================================================== sampler pieces
+struct Cand {
+  float v;
+  int i;
+};
+NT_DEVINL bool cand_before(const Cand& a, const Cand& b) { return a.v > b.v || (a.v == b.v && a.i < b.i); }
+
+// full descending bitonic sort of n (power of two) candidates in shared memory
+template <typename Sync>
+NT_DEVINL void bitonic_sort_desc(Cand* a, int n, Sync sync) {
+  const int tid = threadIdx.x;
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (n >> 1); t += kConsumerThreads) {
+        const int i = ((t / j) * 2 * j) + (t % j);
+        const int l = i + j;
+        const bool desc = ((i & k) == 0);
+        const Cand x = a[i], y = a[l];
+        const bool swap = desc ? cand_before(y, x) : cand_before(x, y);
+        if (swap) a[i] = y, a[l] = x;
+      }
+      sync();
+    }
+  }
+}
+
+NT_DEVINL void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr[0]), lo0 = 0xD2511F53u * ctr[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr[2]), lo1 = 0xCD9E8D57u * ctr[2];
+    const uint32_t n0 = hi1 ^ ctr[1] ^ k0, n1 = lo1, n2 = hi0 ^ ctr[3] ^ k1, n3 = lo0;
+    ctr[0] = n0, ctr[1] = n1, ctr[2] = n2, ctr[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+constexpr int kTopChunk = 2048;
+constexpr int kTopKeep = 64;
+
+// order-preserving float -> uint key (larger float <=> larger key; -inf is the smallest finite key)
+NT_DEVINL uint32_t f2key(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// Block-wide radix select (4 passes of 8 bits, MSB first) over n keys in shared memory: finds the
+// key of the k-th largest element and how many elements equal to it belong to the top-k.
+// scratch: >= 258 uint32.
+template <typename Sync>
+NT_DEVINL void radix_select_kth(const uint32_t* keys, int n, int k, uint32_t* scratch, uint32_t& thr, int& take_eq, Sync sync) {
+  uint32_t* hist = scratch;       // [256]
+  uint32_t* sel = scratch + 256;  // [2]: bin, remaining
+  const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t prefix = 0, mask = 0;
+  int remaining = k;
+  const int n_pad = (n + 31) & ~31;
+#pragma unroll 1
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 256; i += kConsumerThreads) hist[i] = 0;
+    sync();
+    for (int i = tid; i < n_pad; i += kConsumerThreads) {
+      uint32_t bin = 0xffffffffu;
+      if (i < n) {
+        const uint32_t key = keys[i];
+        if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+      }
+      // one shared-memory atomic per distinct bin per warp (logits crowd into few top-byte bins)
+      const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+      if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+    }
+    sync();
+    if (tid < 32) {
+      uint32_t c[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c[j] = hist[8 * lane + j];
+        sum += c[j];
+      }
+      uint32_t suf = sum;  // elements in bins >= 8*lane
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, suf, off);
+        if (lane + off < 32) suf += t;
+      }
+      const uint32_t above = suf - sum;
+      if (above < static_cast<uint32_t>(remaining) && static_cast<uint32_t>(remaining) <= suf) {
+        uint32_t acc = above;
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+          if (acc + c[j] >= static_cast<uint32_t>(remaining)) {
+            sel[0] = 8 * lane + j;
+            sel[1] = remaining - acc;
+            break;
+          }
+          acc += c[j];
+        }
+      }
+    }
+    sync();
+    prefix |= sel[0] << shift;
+    mask |= 0xffu << shift;
+    remaining = static_cast<int>(sel[1]);
+    sync();
+  }
+  thr = prefix;
+  take_eq = remaining;
+}
+
+// Deterministic compaction of the top-k winners (keys > thr, plus the first take_eq keys == thr in
+// index order) into slots [0, k).  scratch: >= 16 uint32.
+template <typename Sync, typename Emit>
+NT_DEVINL void compact_topk(const uint32_t* keys, int n, uint32_t thr, int take_eq, uint32_t* scratch, Sync sync, Emit emit) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (n + kConsumerThreads - 1) / kConsumerThreads;
+  const int lo = min(n, tid * per), hi = min(n, lo + per);
+  int ngt = 0, neq = 0;
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t key = keys[i];
+    ngt += key > thr;
+    neq += key == thr;
+  }
+  int sgt = ngt, seq = neq;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int a = __shfl_up_sync(0xffffffffu, sgt, off), b = __shfl_up_sync(0xffffffffu, seq, off);
+    if (lane >= off) sgt += a, seq += b;
+  }
+  uint32_t* wg = scratch;      // [8] per-warp totals (greater)
+  uint32_t* we = scratch + 8;  // [8] per-warp totals (equal)
+  sync();
+  if (lane == 31) wg[warp] = sgt, we[warp] = seq;
+  sync();
+  int bg = 0, be = 0, total_gt = 0;
+  for (int w = 0; w < kConsumerWarps; ++w) {
+    if (w < warp) bg += wg[w], be += we[w];
+    total_gt += wg[w];
+  }
+  int pos_gt = bg + sgt - ngt;
+  int idx_eq = be + seq - neq;
+  for (int i = lo; i < hi; ++i) {
+    const uint32_t key = keys[i];
+    if (key > thr) {
+      emit(pos_gt++, i);
+    } else if (key == thr) {
+      if (idx_eq < take_eq) emit(total_gt + idx_eq, i);
+      ++idx_eq;
+    }
+  }
+}
+
+// Sampler stage 1 for one (sequence b, chunk): logits processors + exact top-64 of a 2048-logit chunk.
+// keys: [kTopChunk] uint32 shared; scratch: [260] uint32 shared.
+template <typename Sync>
+NT_DEVINL void sample_stage1_chunk(const SamplerParams& p, int b, int chunk, uint32_t* keys, uint32_t* scratch, Sync sync) {
+  const int tid = threadIdx.x;
+  const int ngen = p.n_generated_override ? __ldcg(p.n_generated_override + b) : __ldcg(p.n_generated + b);
+  const bool mask_eos = ngen < p.sp.min_new_tokens;
+  const float inv_t = 1.0f / p.sp.temperature;
+  const float* lg = p.logits + static_cast<long long>(b) * p.V;
+  const int base = chunk * kTopChunk;
+  const int n = min(kTopChunk, p.V - base);
+  sync();  // keys/scratch may still be in use by the previous call of this CTA
+  for (int e = tid; e < n; e += kConsumerThreads) {
+    float v = __ldcg(lg + base + e);
+    if (mask_eos && base + e == p.sp.eos_id) v = -INFINITY;  // MinNewTokensLength
+    keys[e] = f2key(v * inv_t);                              // Temperature
+  }
+  sync();
+  const long long o = (static_cast<long long>(b) * p.nchunks + chunk) * kTopKeep;
+  const int k = min(kTopKeep, n);
+  uint32_t thr;
+  int take_eq;
+  radix_select_kth(keys, n, k, scratch, thr, take_eq, sync);
+  compact_topk(keys, n, thr, take_eq, scratch, sync, [&](int slot, int i) {
+    p.cand_val[o + slot] = __ldcg(lg + base + i);  // raw logit; stage 2 re-applies the processors
+    p.cand_idx[o + slot] = base + i;
+  });
+  for (int s = k + tid; s < kTopKeep; s += kConsumerThreads) {
+    p.cand_val[o + s] = -INFINITY;
+    p.cand_idx[o + s] = 0x7fffffff;
+  }
+}
+
+// Sampler stage 2 for sequence b: top-k of the candidates, softmax, draw, state update, next embedding.
+// keys: [ncand] uint32 shared; scratch: [260]; win: [kTopKeep]; s_tok: shared int.
+template <typename Sync>
+NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint32_t* keys, uint32_t* scratch, Cand* win, int* s_tok,
+                                 Sync sync) {
+  const int tid = threadIdx.x;
+  const bool stateless = p.n_generated_override != nullptr;
+  const int ngen = stateless ? __ldcg(p.n_generated_override + b) : __ldcg(p.n_generated + b);
+  const bool is_done = stateless ? false : (__ldcg(p.done + b) != 0);
+  const bool mask_eos = ngen < p.sp.min_new_tokens;
+  const float inv_t = 1.0f / p.sp.temperature;
+  const float* cv = p.cand_val + static_cast<long long>(b) * ncand;
+  const int32_t* ci = p.cand_idx + static_cast<long long>(b) * ncand;
+  sync();
+  for (int e = tid; e < ncand; e += kConsumerThreads) {
+    float v = __ldcg(cv + e);
+    if (mask_eos && __ldcg(ci + e) == p.sp.eos_id) v = -INFINITY;
+    keys[e] = f2key(v * inv_t);
+  }
+  if (tid < kTopKeep) win[tid].v = -INFINITY, win[tid].i = 0x7fffffff;
+  sync();
+  const int k = min(min(p.sp.top_k, kTopKeep), ncand);
+  uint32_t thr;
+  int take_eq;
+  radix_select_kth(keys, ncand, k, scratch, thr, take_eq, sync);
+  compact_topk(keys, ncand, thr, take_eq, scratch, sync, [&](int slot, int i) {
+    float v = __ldcg(cv + i);
+    const int idx = __ldcg(ci + i);
+    if (mask_eos && idx == p.sp.eos_id) v = -INFINITY;
+    win[slot].v = v * inv_t;
+    win[slot].i = idx;
+  });
+  sync();
+  bitonic_sort_desc(win, kTopKeep, sync);  // 64 winners: (score desc, index asc)
+
+  if (tid < 32) {
+    // softmax over the k kept scores (TopK processor + softmax, utils.py:2789)
+    const float m = win[0].v;
+    const float e0 = (tid < k) ? __expf(win[tid].v - m) : 0.f;
+    const float e1 = (tid + 32 < k) ? __expf(win[tid + 32].v - m) : 0.f;
+    const float sum = warp_sum(e0 + e1);
+    if (p.dbg_topk_val) {
+      p.dbg_topk_val[b * kTopKeep + tid] = (tid < k) ? e0 / sum : 0.f;
+      p.dbg_topk_val[b * kTopKeep + tid + 32] = (tid + 32 < k) ? e1 / sum : 0.f;
+      p.dbg_topk_idx[b * kTopKeep + tid] = (tid < k) ? win[tid].i : -1;
+      p.dbg_topk_idx[b * kTopKeep + tid + 32] = (tid + 32 < k) ? win[tid + 32].i : -1;
+    }
+    if (tid == 0) {
+      int tok;
+      if (p.sp.forced && !stateless) {
+        tok = p.sp.forced[static_cast<long long>(b) * p.max_new + ngen];
+      } else if (p.sp.greedy) {
+        tok = win[0].i;
+      } else {
+        uint32_t ctr[4] = {static_cast<uint32_t>(stateless ? p.step_override : ngen), static_cast<uint32_t>(b), 0u, 0u};
+        philox4x32_10(ctr, static_cast<uint32_t>(p.sp.seed), static_cast<uint32_t>(p.sp.seed >> 32));
+        const float u = (ctr[0] >> 8) * (1.0f / 16777216.0f);  // [0,1)
+        const float target = u * sum;
+        float cum = 0.f;
+        tok = win[k - 1].i;
+        for (int j = 0; j < k; ++j) {
+          cum += __expf(win[j].v - m);
+          if (cum > target) {
+            tok = win[j].i;
+            break;
+          }
+        }
+      }
+      *s_tok = tok;
+      if (p.dbg_token) p.dbg_token[b] = tok;
+      if (!stateless && !is_done) {
+        p.out_tokens[static_cast<long long>(b) * p.max_new + ngen] = tok;
+        p.n_generated[b] = ngen + 1;
+        p.cur_token[b] = tok;
+        const int cached = __ldcg(p.seq_lens + b) + p.advance;  // decode: this step's input token is now in the KV cache
+        if (p.advance) p.seq_lens[b] = cached;
+        const int total = cached + 1;  // tokens in context once `tok` is appended
+        if (tok == p.sp.eos_id || ngen + 1 >= p.sp.max_new_tokens || ngen + 1 >= p.max_new || total >= p.max_ctx)
+          p.done[b] = 1;
+      }
+    }
+  }
+  sync();
+  if (!stateless && !is_done && p.h) {
+    const int tok = *s_tok;
+    const __nv_bfloat16* e = p.embed + static_cast<long long>(tok) * p.hidden;
+    for (int i = tid; i < p.hidden; i += kConsumerThreads) p.h[static_cast<long long>(b) * p.hidden + i] = __bfloat162float(e[i]);
+  }
+}
+
+}  // namespace nt

@@ -85,6 +85,7 @@ struct SamplerParams {
   int32_t step_override;
 };
 int launch_sampler(const SamplerParams& p, int B, cudaStream_t stream);
+int launch_sampler_check(const SamplerParams& p);
 size_t sampler_scratch_floats(int B, int V);  // per-array element count for cand_val / cand_idx
 int sampler_nchunks(int V);
 

@@ -1,0 +1,291 @@
+// Persistent decode megakernel (batch <= 4): ALL layers, the lm_head, the sampler and the whole
+// multi-step decode loop run in one cooperative launch of one CTA per SM.
+//
+//   * one producer warp per CTA streams this CTA's slice of every weight matrix, in phase order,
+//     HBM -> shared memory with cp.async.bulk into a deep mbarrier ring (~170 KB in flight per SM);
+//     weights are immutable, so the stream runs ahead across phase boundaries and hides the grid
+//     barriers;
+//   * eight consumer warps execute the phases (fused RMSNorm + QKV GEMV + bias + RoPE + KV-page
+//     append | split-KV GQA attention | o_proj + residual | RMSNorm + gate/up + SiLU*up | down +
+//     residual | lm_head | radix-select top-k + multinomial draw + next embedding) and meet at a
+//     grid-wide barrier (one L2 atomic + acquire spin) between dependent phases;
+//   * no host involvement between tokens: stop flags, KV lengths and sampled ids live on the device.
+//
+// Replaces the per-token loop of transformers generation/utils.py:2743-2805 (one host sync per
+// step there) and the ~25 ATen launches per layer listed in SURVEY.md §2.1.
+#include "lm_device.cuh"
+#include "lm_mega.cuh"
+
+namespace nt {
+
+NT_DEVINL unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// consumer warps only (256 threads); thread 0 carries the monotonically growing target
+NT_DEVINL void grid_sync(unsigned* gbar, unsigned& target, unsigned nblocks) {
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (threadIdx.x == 0) {
+    target += nblocks;
+    __threadfence();
+    atomicAdd(gbar, 1u);
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(gbar) < target) {
+      if (++spins > (1u << 26)) {
+        printf("neutts_b200: grid barrier timed out (block %d, target %u, seen %u)\n", blockIdx.x, target, *gbar);
+        __trap();
+      }
+    }
+    __threadfence();
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+struct PhaseSlice {
+  int u_begin, my_units, ups, stages, unit_bytes;
+};
+NT_DEVINL PhaseSlice phase_slice(const MegaPhase& ph) {
+  PhaseSlice s;
+  const int nunits = ph.rows >> 1;
+  s.u_begin = static_cast<int>((static_cast<long long>(nunits) * blockIdx.x) / gridDim.x);
+  const int u_end = static_cast<int>((static_cast<long long>(nunits) * (blockIdx.x + 1)) / gridDim.x);
+  s.my_units = u_end - s.u_begin;
+  s.ups = (ph.K >= 2048) ? 1 : kConsumerWarps;
+  s.stages = (s.my_units + s.ups - 1) / s.ups;
+  s.unit_bytes = 4 * ph.K;
+  return s;
+}
+
+template <int NB>
+__global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kernel(const MegaParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* ring = smem + P.ring_off;
+  float4* xs = reinterpret_cast<float4*>(smem + P.x_off);
+  uint8_t* uni = smem + P.union_off;  // AttnSmem  |  sampler keys + scratch + winners
+  float* red = reinterpret_cast<float*>(smem + P.misc_off);
+  float* s_part = red + 2 * kConsumerWarps * 2 * 4;
+  float* s_scale = s_part + kConsumerWarps * 4;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P.bar_off);
+  uint64_t* empty_bar = full_bar + 8;
+  AttnSync* async_ = reinterpret_cast<AttnSync*>(empty_bar + 8);
+  volatile int* s_go = reinterpret_cast<volatile int*>(async_ + 1);  // producer gate: steps released so far, -1 = stop
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NS = P.nstages;
+  const int L = P.n_layers;
+  const int n_phases = 4 * L + 1;
+  AttnSmem* asmem = reinterpret_cast<AttnSmem*>(uni);
+
+  if (tid == 0) {
+    for (int s = 0; s < NS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kConsumerWarps);
+    }
+    mbar_init(&async_->bar, 1);
+    async_->uses = 0;
+    fence_barrier_init();
+    *s_go = 1;
+  }
+  __syncthreads();
+
+  if (warp == kConsumerWarps) {
+    // ============================================================ producer warp
+    if (lane == 0) {
+      uint32_t g = 0;  // global stage counter (ring position)
+      for (int step = 0; step < P.n_steps; ++step) {
+        uint32_t spins = 0;
+        int go;
+        while ((go = *s_go) >= 0 && go <= step) {  // released one step at a time (early exit safety)
+          __nanosleep(64);
+          if (++spins > (1u << 26)) {
+            printf("neutts_b200: producer gate timed out (block %d)\n", blockIdx.x);
+            __trap();
+          }
+        }
+        if (go < 0) break;
+        for (int ph = 0; ph < n_phases; ++ph) {
+          const int pidx = (ph == n_phases - 1) ? (4 * P.total_layers) : ph;  // lm_head is the last table entry
+          const MegaPhase mp = P.phases[pidx];
+          const PhaseSlice sl = phase_slice(mp);
+          const uint8_t* wbase = reinterpret_cast<const uint8_t*>(mp.W) + static_cast<long long>(sl.u_begin) * sl.unit_bytes;
+          for (int it = 0; it < sl.stages; ++it, ++g) {
+            const int slot = g % NS;
+            if (g >= static_cast<uint32_t>(NS)) mbar_wait(&empty_bar[slot], ((g / NS) - 1) & 1);
+            const int u0 = it * sl.ups;
+            const uint32_t bytes = static_cast<uint32_t>(min(sl.ups, sl.my_units - u0)) * sl.unit_bytes;
+            mbar_arrive_expect_tx(&full_bar[slot], bytes);
+            bulk_g2s(ring + static_cast<size_t>(slot) * P.stage_bytes, wbase + static_cast<long long>(u0) * sl.unit_bytes, bytes,
+                     &full_bar[slot]);
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ============================================================== consumer warps
+  uint32_t g = 0;
+  unsigned target = 0;
+  const unsigned G = gridDim.x;
+
+  auto gemv_phase = [&](const GemvParams& gp, int pidx) {
+    const MegaPhase mp = P.phases[pidx];
+    const PhaseSlice sl = phase_slice(mp);
+    load_x_planes<NB>(gp.x, gp.ldx, gp.K, gp.norm_w, gp.eps, xs, s_part, s_scale, SyncConsumers());
+    for (int it = 0; it < sl.stages; ++it, ++g) {
+      const int slot = g % NS;
+      mbar_wait(&full_bar[slot], (g / NS) & 1);
+      const int first = it * sl.ups;
+      gemv_consume_stage<NB>(gp, ring + static_cast<size_t>(slot) * P.stage_bytes, xs, red, sl.ups == 1 ? kConsumerWarps : 1, first,
+                             min(sl.ups, sl.my_units - first), sl.u_begin, it & 1, [&]() {
+                               if (lane == 0) mbar_arrive(&empty_bar[slot]);
+                             });
+    }
+  };
+
+  const int H = P.hidden, I = P.inter, HD = P.n_heads * 64;
+  for (int step = 0; step < P.n_steps; ++step) {
+    for (int l = 0; l < L; ++l) {
+      GemvParams gp;
+      // ---- QKV: fused RMSNorm + bias + RoPE + KV-page append
+      gp = GemvParams{};
+      gp.W = P.phases[4 * l + 0].W, gp.rows = P.qkv_n, gp.K = H, gp.x = P.h, gp.ldx = H;
+      gp.norm_w = P.ln1[l], gp.eps = P.eps, gp.bias = P.bqkv[l];
+      gp.epi = GEMV_QKV_ROPE, gp.q_out = P.q, gp.kv = P.kv, gp.layer = l, gp.n_heads = P.n_heads, gp.inv_freq = P.inv_freq;
+      gemv_phase(gp, 4 * l + 0);
+      grid_sync(P.gbar, target, G);
+      // ---- split-KV attention: items (b, kv head, split) round-robin over the CTAs
+      {
+        AttnDecParams ap;
+        ap.q = P.q, ap.kv = P.kv, ap.layer = l, ap.n_heads = P.n_heads, ap.n_rep = P.n_heads / P.kv.n_kv_heads;
+        ap.scale_log2 = P.scale_log2, ap.part_o = P.part_o, ap.part_ml = P.part_ml, ap.counters = P.counters;
+        ap.out = P.attn, ap.out_bf16 = nullptr, ap.max_splits = P.max_splits;
+        const int per_b = P.kv.n_kv_heads * P.max_splits;
+        for (int item = blockIdx.x; item < NB * per_b; item += G) {
+          const int b = item / per_b, r = item - b * per_b;
+          const int kvh = r / P.max_splits, split = r - kvh * P.max_splits;
+          const int n_ctx = min(__ldcg(P.kv.seq_lens + b) + 1, P.kv.max_ctx);
+          const int nsplit = (n_ctx + 63) >> 6;
+          if (split < nsplit) attn_decode_item(ap, b, kvh, split, n_ctx, nsplit, asmem, async_, SyncConsumers());
+        }
+      }
+      grid_sync(P.gbar, target, G);
+      // ---- o_proj + residual
+      gp = GemvParams{};
+      gp.W = P.phases[4 * l + 1].W, gp.rows = H, gp.K = HD, gp.x = P.attn, gp.ldx = HD;
+      gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
+      gemv_phase(gp, 4 * l + 1);
+      grid_sync(P.gbar, target, G);
+      // ---- RMSNorm + gate/up + SiLU*up
+      gp = GemvParams{};
+      gp.W = P.phases[4 * l + 2].W, gp.rows = 2 * I, gp.K = H, gp.x = P.h, gp.ldx = H;
+      gp.norm_w = P.ln2[l], gp.eps = P.eps, gp.epi = GEMV_SWIGLU, gp.out = P.act, gp.ldo = I;
+      gemv_phase(gp, 4 * l + 2);
+      grid_sync(P.gbar, target, G);
+      // ---- down + residual
+      gp = GemvParams{};
+      gp.W = P.phases[4 * l + 3].W, gp.rows = H, gp.K = I, gp.x = P.act, gp.ldx = I;
+      gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
+      gemv_phase(gp, 4 * l + 3);
+      grid_sync(P.gbar, target, G);
+    }
+    // ---- lm_head (fused final RMSNorm)
+    {
+      GemvParams gp{};
+      gp.W = P.phases[4 * P.total_layers].W, gp.rows = P.vocab, gp.K = H, gp.x = P.h, gp.ldx = H;
+      gp.norm_w = P.final_norm, gp.eps = P.eps, gp.epi = GEMV_STORE, gp.out = P.logits, gp.ldo = P.vocab;
+      gemv_phase(gp, 4 * P.total_layers);
+    }
+    grid_sync(P.gbar, target, G);
+    if (P.logits_out) {  // tests: keep every step's logits
+      const long long n = static_cast<long long>(NB) * P.vocab;
+      float* dst = P.logits_out + static_cast<long long>(step) * n;
+      for (long long i = static_cast<long long>(blockIdx.x) * kConsumerThreads + tid; i < n; i += static_cast<long long>(G) * kConsumerThreads)
+        dst[i] = __ldcg(P.logits + i);
+    }
+    // ---- sampler stage 1: per-chunk top-64 (radix select), chunks round-robin over the CTAs
+    {
+      uint32_t* keys = reinterpret_cast<uint32_t*>(uni);
+      uint32_t* scratch = keys + P.samp_keys;
+      for (int item = blockIdx.x; item < NB * P.samp.nchunks; item += G)
+        sample_stage1_chunk(P.samp, item / P.samp.nchunks, item % P.samp.nchunks, keys, scratch, SyncConsumers());
+    }
+    grid_sync(P.gbar, target, G);
+    // ---- sampler stage 2: CTA b finishes sequence b (top-k, softmax, draw, state, next embedding)
+    if (static_cast<int>(blockIdx.x) < NB) {
+      uint32_t* keys = reinterpret_cast<uint32_t*>(uni);
+      uint32_t* scratch = keys + P.samp_keys;
+      Cand* win = reinterpret_cast<Cand*>(scratch + 260);
+      int* s_tok = reinterpret_cast<int*>(win + kTopKeep);
+      sample_stage2_seq(P.samp, blockIdx.x, P.samp.nchunks * kTopKeep, keys, scratch, win, s_tok, SyncConsumers());
+    }
+    grid_sync(P.gbar, target, G);
+    // ---- stop when every sequence is finished (same decision in every CTA: flags were published before the barrier)
+    bool all_done = true;
+    for (int b = 0; b < NB; ++b) all_done = all_done && (__ldcg(P.samp.done + b) != 0);
+    if (all_done || step + 1 == P.n_steps) break;
+    if (tid == 0) *s_go = step + 2;  // release the producer into the next step
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  if (tid == 0) *s_go = -1;
+}
+
+int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream) {
+  if (nb < 1 || nb > 4) return set_error(NT_ERR_INVALID, "megakernel: batch %d not in 1..4", nb);
+  // shared-memory plan
+  const int k_small = P.hidden, k_big = P.inter > P.n_heads * 64 ? P.inter : P.n_heads * 64;
+  auto unit_stage = [](int K) { return (K >= 2048 ? 1 : kConsumerWarps) * 4 * K; };
+  int stage = unit_stage(k_small);
+  if (unit_stage(k_big) > stage) stage = unit_stage(k_big);
+  if (unit_stage(P.n_heads * 64) > stage) stage = unit_stage(P.n_heads * 64);
+  stage = (stage + 127) & ~127;
+  const size_t x_bytes = size_t(nb) * (k_big > k_small ? k_big : k_small) * 4;
+  const int ncand = P.samp.nchunks * kTopKeep;
+  P.samp_keys = ncand > kTopChunk ? ncand : kTopChunk;
+  size_t uni = size_t(P.samp_keys) * 4 + 260 * 4 + kTopKeep * sizeof(Cand) + 16;
+  if (sizeof(AttnSmem) > uni) uni = sizeof(AttnSmem);
+  uni = (uni + 127) & ~size_t(127);
+  const size_t misc = (2 * kConsumerWarps * 2 * 4 + kConsumerWarps * 4 + 4) * sizeof(float);
+  const size_t bars = 16 * sizeof(uint64_t) + sizeof(AttnSync) + 16;
+  const size_t fixed = ((x_bytes + 127) & ~size_t(127)) + uni + ((misc + 127) & ~size_t(127)) + bars + 128;
+  const size_t budget = 227 * 1024;
+  if (fixed + 2 * size_t(stage) > budget) return set_error(NT_ERR_INVALID, "megakernel: model does not fit the shared-memory plan");
+  int ns = int((budget - fixed) / stage);
+  if (ns > 8) ns = 8;
+  P.nstages = ns;
+  P.stage_bytes = stage;
+  size_t off = 0;
+  P.ring_off = off, off += size_t(ns) * stage;
+  P.x_off = off, off += (x_bytes + 127) & ~size_t(127);
+  P.union_off = off, off += uni;
+  P.misc_off = off, off += (misc + 127) & ~size_t(127);
+  P.bar_off = off, off += bars;
+  const size_t smem = off + 128;
+
+  void (*kern)(const MegaParams) = nullptr;
+  switch (nb) {
+    case 1: kern = decode_mega_kernel<1>; break;
+    case 2: kern = decode_mega_kernel<2>; break;
+    case 3: kern = decode_mega_kernel<3>; break;
+    default: kern = decode_mega_kernel<4>; break;
+  }
+  static size_t attr[5] = {0, 0, 0, 0, 0};
+  if (attr[nb] < smem) {
+    NT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    attr[nb] = smem;
+  }
+  int per_sm = 0;
+  NT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (kConsumerWarps + 1) * 32, smem));
+  if (per_sm < 1) return set_error(NT_ERR_CUDA, "megakernel: a CTA does not fit on an SM (%zu B shared memory)", smem);
+  NT_CUDA_CHECK(cudaMemsetAsync(P.gbar, 0, sizeof(unsigned), stream));
+  void* args[] = {&P};
+  cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(num_sms), dim3((kConsumerWarps + 1) * 32), args, smem, stream);
+  if (e != cudaSuccess) return set_error(NT_ERR_CUDA, "megakernel launch failed: %s", cudaGetErrorString(e));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return NT_OK;
+}
+
+}  // namespace nt
