@@ -11,10 +11,11 @@
 #define NT_DEVINL __device__ __forceinline__
 
 // Spin bound for every mbarrier wait: a protocol bug becomes a trap (the launch fails with
-// an error the host reports) instead of a hung GPU box.  ~2^28 polls with backoff >> any
-// legitimate wait in these kernels.
+// an error the host reports) instead of a hung GPU box.  try_wait itself suspends the thread for
+// a hardware-defined slice per call, so 2^22 tries is seconds — far beyond any legitimate wait
+// in these kernels (the longest is one decode step, ~1 ms).
 #ifndef NT_SPIN_LIMIT
-#define NT_SPIN_LIMIT (1u << 28)
+#define NT_SPIN_LIMIT (1u << 22)
 #endif
 
 namespace nt {

@@ -69,6 +69,8 @@ struct nt_lm {
   uint64_t graph_kernels = 0;         // kernel nodes in the captured step (for nt_launch_count)
   bool prefilled = false;
   int debug_layers = -1;              // >= 0: run only this many layers (per-stage parity tests)
+  long long* prof = nullptr;          // megakernel timeline buffer (profiles/probe_mega.py)
+  int prof_step = 0;
 };
 
 template <typename F>
@@ -107,7 +109,7 @@ static size_t lm_carve(const nt_lm_config& c, void* ws, size_t bytes, F&& assign
     (L)->act_bf16 = a.take<__nv_bfloat16>(size_t(rows) * I);                                   \
     (L)->phase_tab = a.take<MegaPhase>(size_t(4) * c.n_layers + 1);                            \
     (L)->ptr_tab = a.take<const float*>(size_t(3) * c.n_layers);                               \
-    (L)->gbar = a.take<unsigned>(64);                                                          \
+    (L)->gbar = a.take<unsigned>(256);                                                         \
   }
 
 static int lm_check_config(const nt_lm_config* c) {
@@ -455,6 +457,7 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
     P.gbar = lm->gbar;
     P.n_steps = n_steps;
     P.logits_out = logits_out;
+    P.prof = lm->prof, P.prof_step = lm->prof_step;
     if ((rc = launch_sampler_check(P.samp))) return rc;
     return launch_decode_mega(P, B, lm->num_sms, stream);
   }
@@ -517,6 +520,12 @@ extern "C" int nt_lm_debug_set_layers(nt_lm* lm, int n_layers) {
     cudaGraphExecDestroy(lm->graph);
     lm->graph = nullptr;
   }
+  return NT_OK;
+}
+extern "C" int nt_lm_debug_set_profile(nt_lm* lm, long long* buf, int step) {
+  if (!lm) return set_error(NT_ERR_INVALID, "nt_lm_debug_set_profile: null handle");
+  lm->prof = buf;
+  lm->prof_step = step;
   return NT_OK;
 }
 extern "C" void* nt_lm_debug_ptr(nt_lm* lm, const char* name) {

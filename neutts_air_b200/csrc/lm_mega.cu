@@ -18,27 +18,54 @@
 
 namespace nt {
 
+NT_DEVINL unsigned ld_relaxed_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 NT_DEVINL unsigned ld_acquire_gpu(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
-// consumer warps only (256 threads); thread 0 carries the monotonically growing target
-NT_DEVINL void grid_sync(unsigned* gbar, unsigned& target, unsigned nblocks) {
+NT_DEVINL long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// optional in-kernel timeline (thread 0 of the first and the last CTA, one chosen step)
+struct Prof {
+  long long* buf;
+  int n;
+  NT_DEVINL void mark() {
+    if (buf && n < kProfMarks) buf[n++] = global_ns();
+  }
+};
+
+// Grid-wide barrier over the consumer warps of all CTAs: one relaxed L2 atomic per CTA on a
+// monotonically growing counter (release fence before it), then thread 0 spins with acquire loads
+// until the counter reaches this barrier's target.  Measured on B200 (profiles/mega_timeline_r1.md):
+// ~0.5 us to publish + ~1.3-2.6 us until the slowest CTA has arrived.  A flag-array variant (one word
+// per CTA, coalesced polling, no atomics) was tried and is 2x slower: 148 pollers hammering the flag
+// lines delay the flag stores themselves.
+NT_DEVINL void grid_sync(unsigned* gbar, unsigned& target, unsigned nblocks, Prof& prof) {
   asm volatile("bar.sync 1, 256;" ::: "memory");
   if (threadIdx.x == 0) {
+    prof.mark();  // all consumer warps of this CTA are done
     target += nblocks;
     __threadfence();
     atomicAdd(gbar, 1u);
+    prof.mark();  // arrival published
     uint32_t spins = 0;
     while (ld_acquire_gpu(gbar) < target) {
-      if (++spins > (1u << 26)) {
+      if (++spins > (1u << 23)) {
         printf("neutts_b200: grid barrier timed out (block %d, target %u, seen %u)\n", blockIdx.x, target, *gbar);
         __trap();
       }
     }
-    __threadfence();
+    prof.mark();  // barrier released
   }
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
@@ -100,7 +127,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
         int go;
         while ((go = *s_go) >= 0 && go <= step) {  // released one step at a time (early exit safety)
           __nanosleep(64);
-          if (++spins > (1u << 26)) {
+          if (++spins > (1u << 25)) {
             printf("neutts_b200: producer gate timed out (block %d)\n", blockIdx.x);
             __trap();
           }
@@ -128,13 +155,15 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
 
   // ============================================================== consumer warps
   uint32_t g = 0;
-  unsigned target = 0;
+  unsigned target = 0;  // barrier epoch (flags are zeroed before every launch)
   const unsigned G = gridDim.x;
+  Prof prof{nullptr, 0};
 
   auto gemv_phase = [&](const GemvParams& gp, int pidx) {
     const MegaPhase mp = P.phases[pidx];
     const PhaseSlice sl = phase_slice(mp);
     load_x_planes<NB>(gp.x, gp.ldx, gp.K, gp.norm_w, gp.eps, xs, s_part, s_scale, SyncConsumers());
+    if (tid == 0) prof.mark();  // input vector staged
     for (int it = 0; it < sl.stages; ++it, ++g) {
       const int slot = g % NS;
       mbar_wait(&full_bar[slot], (g / NS) & 1);
@@ -148,6 +177,13 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
 
   const int H = P.hidden, I = P.inter, HD = P.n_heads * 64;
   for (int step = 0; step < P.n_steps; ++step) {
+    if (P.prof && tid == 0 && step == P.prof_step && (blockIdx.x == 0 || blockIdx.x == G - 1)) {
+      prof.buf = P.prof + (blockIdx.x == 0 ? 0 : kProfMarks);
+      prof.n = 0;
+      prof.mark();
+    } else {
+      prof.buf = nullptr;
+    }
     for (int l = 0; l < L; ++l) {
       GemvParams gp;
       // ---- QKV: fused RMSNorm + bias + RoPE + KV-page append
@@ -156,7 +192,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       gp.norm_w = P.ln1[l], gp.eps = P.eps, gp.bias = P.bqkv[l];
       gp.epi = GEMV_QKV_ROPE, gp.q_out = P.q, gp.kv = P.kv, gp.layer = l, gp.n_heads = P.n_heads, gp.inv_freq = P.inv_freq;
       gemv_phase(gp, 4 * l + 0);
-      grid_sync(P.gbar, target, G);
+      grid_sync(P.gbar, target, G, prof);
       // ---- split-KV attention: items (b, kv head, split) round-robin over the CTAs
       {
         AttnDecParams ap;
@@ -172,25 +208,25 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
           if (split < nsplit) attn_decode_item(ap, b, kvh, split, n_ctx, nsplit, asmem, async_, SyncConsumers());
         }
       }
-      grid_sync(P.gbar, target, G);
+      grid_sync(P.gbar, target, G, prof);
       // ---- o_proj + residual
       gp = GemvParams{};
       gp.W = P.phases[4 * l + 1].W, gp.rows = H, gp.K = HD, gp.x = P.attn, gp.ldx = HD;
       gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
       gemv_phase(gp, 4 * l + 1);
-      grid_sync(P.gbar, target, G);
+      grid_sync(P.gbar, target, G, prof);
       // ---- RMSNorm + gate/up + SiLU*up
       gp = GemvParams{};
       gp.W = P.phases[4 * l + 2].W, gp.rows = 2 * I, gp.K = H, gp.x = P.h, gp.ldx = H;
       gp.norm_w = P.ln2[l], gp.eps = P.eps, gp.epi = GEMV_SWIGLU, gp.out = P.act, gp.ldo = I;
       gemv_phase(gp, 4 * l + 2);
-      grid_sync(P.gbar, target, G);
+      grid_sync(P.gbar, target, G, prof);
       // ---- down + residual
       gp = GemvParams{};
       gp.W = P.phases[4 * l + 3].W, gp.rows = H, gp.K = I, gp.x = P.act, gp.ldx = I;
       gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
       gemv_phase(gp, 4 * l + 3);
-      grid_sync(P.gbar, target, G);
+      grid_sync(P.gbar, target, G, prof);
     }
     // ---- lm_head (fused final RMSNorm)
     {
@@ -199,7 +235,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       gp.norm_w = P.final_norm, gp.eps = P.eps, gp.epi = GEMV_STORE, gp.out = P.logits, gp.ldo = P.vocab;
       gemv_phase(gp, 4 * P.total_layers);
     }
-    grid_sync(P.gbar, target, G);
+    grid_sync(P.gbar, target, G, prof);
     if (P.logits_out) {  // tests: keep every step's logits
       const long long n = static_cast<long long>(NB) * P.vocab;
       float* dst = P.logits_out + static_cast<long long>(step) * n;
@@ -213,7 +249,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       for (int item = blockIdx.x; item < NB * P.samp.nchunks; item += G)
         sample_stage1_chunk(P.samp, item / P.samp.nchunks, item % P.samp.nchunks, keys, scratch, SyncConsumers());
     }
-    grid_sync(P.gbar, target, G);
+    grid_sync(P.gbar, target, G, prof);
     // ---- sampler stage 2: CTA b finishes sequence b (top-k, softmax, draw, state, next embedding)
     if (static_cast<int>(blockIdx.x) < NB) {
       uint32_t* keys = reinterpret_cast<uint32_t*>(uni);
@@ -222,7 +258,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       int* s_tok = reinterpret_cast<int*>(win + kTopKeep);
       sample_stage2_seq(P.samp, blockIdx.x, P.samp.nchunks * kTopKeep, keys, scratch, win, s_tok, SyncConsumers());
     }
-    grid_sync(P.gbar, target, G);
+    grid_sync(P.gbar, target, G, prof);
     // ---- stop when every sequence is finished (same decision in every CTA: flags were published before the barrier)
     bool all_done = true;
     for (int b = 0; b < NB; ++b) all_done = all_done && (__ldcg(P.samp.done + b) != 0);
@@ -235,6 +271,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
 
 int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream) {
   if (nb < 1 || nb > 4) return set_error(NT_ERR_INVALID, "megakernel: batch %d not in 1..4", nb);
+  if (num_sms > 256) num_sms = 256;  // size of the barrier flag array
   // shared-memory plan
   const int k_small = P.hidden, k_big = P.inter > P.n_heads * 64 ? P.inter : P.n_heads * 64;
   auto unit_stage = [](int K) { return (K >= 2048 ? 1 : kConsumerWarps) * 4 * K; };
@@ -280,7 +317,7 @@ int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream) 
   int per_sm = 0;
   NT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (kConsumerWarps + 1) * 32, smem));
   if (per_sm < 1) return set_error(NT_ERR_CUDA, "megakernel: a CTA does not fit on an SM (%zu B shared memory)", smem);
-  NT_CUDA_CHECK(cudaMemsetAsync(P.gbar, 0, sizeof(unsigned), stream));
+  NT_CUDA_CHECK(cudaMemsetAsync(P.gbar, 0, sizeof(unsigned) * 256, stream));
   void* args[] = {&P};
   cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(num_sms), dim3((kConsumerWarps + 1) * 32), args, smem, stream);
   if (e != cudaSuccess) return set_error(NT_ERR_CUDA, "megakernel launch failed: %s", cudaGetErrorString(e));

@@ -31,11 +31,14 @@ struct MegaParams {
   unsigned* gbar;     // grid barrier counter, zeroed before every launch
   int n_steps;
   float* logits_out;  // optional [n_steps][nb][vocab]
+  long long* prof;    // optional timeline buffer [2 CTAs][kProfMarks] of %globaltimer ns (profiles/probe_mega.py)
+  int prof_step;
   // shared-memory plan (filled by launch_decode_mega)
   int nstages, stage_bytes, samp_keys;
   size_t ring_off, x_off, union_off, misc_off, bar_off;
 };
 
+constexpr int kProfMarks = 1024;
 int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream);
 
 }  // namespace nt

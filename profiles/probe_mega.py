@@ -1,0 +1,39 @@
+"""In-kernel timeline of one decode step of the persistent megakernel (first and last CTA).
+Marks per GEMV phase: [x staged] ... then per grid barrier: [CTA done] [arrival published] [released]."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from neutts_air_b200 import synthetic, _lib
+from neutts_air_b200.lm import LMShape, SpeechLM
+
+layers = int(os.environ.get("LAYERS", "24"))
+shape = LMShape(num_layers=layers)
+lm = SpeechLM(shape, synthetic.lm_state_dict(shape, 0), device="cuda:0", max_batch=1, max_ctx=2048, max_new=64, max_prefill_tokens=512)
+buf = torch.zeros(2, 1024, dtype=torch.int64, device="cuda:0")
+_lib.check(lm.L.nt_lm_debug_set_profile(lm.handle, buf.data_ptr(), 10))
+print("engine built", flush=True)
+sp = lm.sampling(151670, min_new_tokens=64, max_new_tokens=40)
+lm.prefill([list(range(100, 600))], sp)
+torch.cuda.synchronize()
+print("prefill done", flush=True)
+lm.decode(30, sp)
+torch.cuda.synchronize()
+print("decode done", flush=True)
+t = buf.cpu().numpy()
+for c in range(2):
+    m = t[c][t[c] > 0]
+    d = np.diff(m) / 1000.0
+    print(f"CTA {'first' if c == 0 else 'last'}: {len(m)} marks, step total {(m[-1]-m[0])/1000:.1f} us")
+    # layout: mark0 = step start; per layer: (x, done, arr, rel) qkv | (done, arr, rel) attn | (x,done,arr,rel) o | gu | d
+    i = 1
+    names = []
+    for l in range(layers):
+        names += [f"L{l}.qkv.x", f"L{l}.qkv.done", f"L{l}.qkv.arr", f"L{l}.qkv.rel", f"L{l}.att.done", f"L{l}.att.arr", f"L{l}.att.rel"]
+        for ph in ("o", "gu", "d"):
+            names += [f"L{l}.{ph}.x", f"L{l}.{ph}.done", f"L{l}.{ph}.arr", f"L{l}.{ph}.rel"]
+    names += ["head.x", "head.done", "head.arr", "head.rel", "s1.done", "s1.arr", "s1.rel", "s2.done", "s2.arr", "s2.rel"]
+    agg = {}
+    for nme, dt in zip(names, d):
+        key = nme.split(".", 1)[1] if nme.startswith("L") else nme
+        agg.setdefault(key, []).append(dt)
+    print({k: round(float(np.mean(v)), 2) for k, v in agg.items()})
