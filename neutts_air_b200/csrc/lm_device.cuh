@@ -28,8 +28,8 @@ NT_DEVINL T ld_cg(const T* p) {
 // x planes: element k = 8c + j of batch row b lives in xs[(2b + j/4) * nch + c] component j%4, so
 // the two float4 reads that pair with one 16-byte bf16 weight chunk are conflict-free.
 template <int NB, typename Sync>
-NT_DEVINL void load_x_planes(const float* x, long long ldx, int K, const float* norm_w, float eps, float4* xs,
-                             float* s_part /*[8][4]*/, float* s_scale /*[4]*/, Sync sync) {
+NT_DEVINL void load_x_planes(const float* x, long long ldx, int K, const float* norm_w /*global or shared*/, float eps, float4* xs,
+                             float* s_part /*[8][4]*/, Sync sync) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nch = K >> 3, nvec = K >> 2;
   float ssq[NB];
@@ -50,27 +50,23 @@ NT_DEVINL void load_x_planes(const float* x, long long ldx, int K, const float* 
       const float t = warp_sum(ssq[b]);
       if (lane == 0) s_part[warp * 4 + b] = t;
     }
-  }
-  sync();
-  if (norm_w) {
-    if (tid < NB) {
-      float t = 0.f;
-      for (int w = 0; w < kConsumerWarps; ++w) t += s_part[w * 4 + tid];
-      s_scale[tid] = rsqrtf(t / static_cast<float>(K) + eps);
-    }
     sync();
+    // every thread rebuilds the row scale from the 8 warp partials and rescales the elements it wrote itself
     const float4* nw = reinterpret_cast<const float4*>(norm_w);
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-      const float sc = s_scale[b];
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kConsumerWarps; ++w) t += s_part[w * 4 + b];
+      const float sc = rsqrtf(t / static_cast<float>(K) + eps);
       for (int m = tid; m < nvec; m += kConsumerThreads) {
         float4& v = xs[(2 * b + (m & 1)) * nch + (m >> 1)];
-        const float4 g = __ldg(nw + m);
+        const float4 g = nw[m];
         v.x = v.x * sc * g.x, v.y = v.y * sc * g.y, v.z = v.z * sc * g.z, v.w = v.w * sc * g.w;
       }
     }
-    sync();
   }
+  sync();
 }
 
 // dot products of one unit (two adjacent bf16 rows in shared memory) with the NB x-vectors over
@@ -104,7 +100,10 @@ NT_DEVINL void gemv_epilogue(const GemvParams& p, int u, float (&d0)[NB], float 
   for (int i = 1; i < NB; ++i)
     if (b == i) a0 = d0[i], a1 = d1[i];
   const int r0 = 2 * u;
-  if (p.bias) {
+  if (p.bias_smem) {
+    a0 += p.bias_smem[r0 - p.row0];
+    a1 += p.bias_smem[r0 - p.row0 + 1];
+  } else if (p.bias) {
     a0 += __ldg(p.bias + r0);
     a1 += __ldg(p.bias + r0 + 1);
   }
@@ -115,12 +114,16 @@ NT_DEVINL void gemv_epilogue(const GemvParams& p, int u, float (&d0)[NB], float 
       a1 += r.y;
     }
     *reinterpret_cast<float2*>(p.out + b * p.ldo + r0) = make_float2(a0, a1);
+    if (p.smem_out) {
+      p.smem_out[b * p.smem_ld + r0 - p.row0] = a0;
+      p.smem_out[b * p.smem_ld + r0 - p.row0 + 1] = a1;
+    }
   } else if (p.epi == GEMV_SWIGLU) {
     p.out[b * p.ldo + u] = silu(a0) * a1;
   } else {  // GEMV_QKV_ROPE
     const int head = u >> 5;  // 32 units per 64-row head
     const int i = u & 31;
-    const int pos = __ldcg(p.kv.seq_lens + b);
+    const int pos = p.pos_cache ? p.pos_cache[b] : __ldcg(p.kv.seq_lens + b);
     const int n_kv = p.kv.n_kv_heads;
     if (head < p.n_heads + n_kv) {
       // rows (i, i+32) of a q/k head: half-split rotation (modeling_qwen2.py:116-146)
@@ -133,13 +136,13 @@ NT_DEVINL void gemv_epilogue(const GemvParams& p, int u, float (&d0)[NB], float 
         q[i] = lo;
         q[i + 32] = hi;
       } else if (pos < p.kv.max_ctx) {
-        const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + (pos >> 6));
+        const int page = p.page_cache ? p.page_cache[b] : __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + (pos >> 6));
         __nv_bfloat16* kp = p.kv.page_ptr(p.layer, 0, page, head - p.n_heads) + (pos & 63) * 64;
         kp[i] = __float2bfloat16(lo);
         kp[i + 32] = __float2bfloat16(hi);
       }
     } else if (pos < p.kv.max_ctx) {
-      const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + (pos >> 6));
+      const int page = p.page_cache ? p.page_cache[b] : __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + (pos >> 6));
       __nv_bfloat16* vp = p.kv.page_ptr(p.layer, 1, page, head - p.n_heads - n_kv) + (pos & 63) * 64;
       *reinterpret_cast<__nv_bfloat162*>(vp + 2 * i) = __floats2bfloat162_rn(a0, a1);
     }
@@ -218,6 +221,7 @@ struct AttnSmem {
   float q[8][64];
   float s[8][64];
   float ml[8][2];
+  float corr[8];
   float red[4][8][64];
 };
 struct AttnSync {      // lives outside any aliased shared-memory region
@@ -338,31 +342,156 @@ NT_DEVINL void attn_decode_item(const AttnDecParams& p, int b, int kvh, int spli
   if (tid == 0) p.counters[b * p.kv.n_kv_heads + kvh] = 0;
 }
 
+// ---- megakernel variant: an item covers `pps` consecutive pages of one (sequence, kv head) with an
+// online softmax across pages and only writes its partial (m, l, unnormalised o); the consumer of
+// the attention output merges the partials itself (load_attn_merged), so there is no atomic /
+// last-arriver chain in the attention phase.
+NT_DEVINL void attn_issue_page(const AttnDecParams& p, int b, int kvh, int page_idx, AttnSmem* sm, AttnSync* sy) {
+  const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + page_idx);
+  asm volatile("fence.proxy.async;" ::: "memory");  // K/V rows may have been written through the generic proxy
+  mbar_arrive_expect_tx(&sy->bar, 2 * 8192);
+  bulk_g2s(sm->k, p.kv.page_ptr(p.layer, 0, page, kvh), 8192, &sy->bar);
+  bulk_g2s(sm->v, p.kv.page_ptr(p.layer, 1, page, kvh), 8192, &sy->bar);
+}
+
+template <typename Sync>
+NT_DEVINL void attn_split_item(const AttnDecParams& p, int b, int kvh, int split, int pps, int npages, int n_ctx, AttnSmem* sm,
+                               AttnSync* sy, bool first_page_in_flight, Sync sync) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_rep = p.n_rep;
+  for (int i = tid; i < n_rep * 64; i += kConsumerThreads)
+    sm->q[i >> 6][i & 63] = __ldcg(p.q + (static_cast<long long>(b) * p.n_heads + kvh * n_rep + (i >> 6)) * 64 + (i & 63));
+  if (tid < 8) sm->ml[tid][0] = -INFINITY, sm->ml[tid][1] = 0.f;
+  float acc[8];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) acc[h] = 0.f;
+  const int p0 = split * pps, p1 = min(p0 + pps, npages);
+  for (int pg = p0; pg < p1; ++pg) {
+    const uint32_t parity = sy->uses & 1;
+    sync();  // previous page fully consumed; q / running stats visible; everyone has read `uses`
+    if (tid == 0) {
+      if (!(first_page_in_flight && pg == p0)) attn_issue_page(p, b, kvh, pg, sm, sy);
+      sy->uses += 1;
+    }
+    mbar_wait(&sy->bar, parity);
+    {  // scores: thread = (token, quarter of the head dim)
+      const int tok = tid >> 2, part = tid & 3;
+      const uint4* kr = reinterpret_cast<const uint4*>(sm->k + tok * 64 + part * 16);
+      float kf[16];
+      {
+        float t[8];
+        bf16x8_to_f32(kr[0], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) kf[j] = t[j];
+        bf16x8_to_f32(kr[1], t);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) kf[8 + j] = t[j];
+      }
+      const bool valid = (pg * 64 + tok) < n_ctx;
+      for (int h = 0; h < n_rep; ++h) {
+        float d = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) d += kf[j] * sm->q[h][part * 16 + j];
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        if (part == 0) sm->s[h][tok] = valid ? d * p.scale_log2 : -INFINITY;
+      }
+    }
+    sync();
+    if (warp < n_rep) {  // online softmax update of head `warp`
+      const float s0 = sm->s[warp][lane], s1 = sm->s[warp][lane + 32];
+      const float m_old = sm->ml[warp][0];
+      const float m_new = fmaxf(m_old, warp_max(fmaxf(s0, s1)));  // every page of a live split has a valid token
+      const float p0v = exp2f(s0 - m_new), p1v = exp2f(s1 - m_new);
+      const float lsum = warp_sum(p0v + p1v);
+      sm->s[warp][lane] = p0v;
+      sm->s[warp][lane + 32] = p1v;
+      if (lane == 0) {
+        const float c = exp2f(m_old - m_new);  // 0 on the first page (m_old = -inf)
+        sm->corr[warp] = c;
+        sm->ml[warp][0] = m_new;
+        sm->ml[warp][1] = sm->ml[warp][1] * c + lsum;
+      }
+    }
+    sync();
+    {  // P.V : thread = (dim, token group of 16), accumulators carried across pages
+      const int d = tid & 63, g = tid >> 6;
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        if (h < n_rep) acc[h] *= sm->corr[h];
+      for (int t = g * 16; t < g * 16 + 16; ++t) {
+        const float v = __bfloat162float(sm->v[t * 64 + d]);
+#pragma unroll
+        for (int h = 0; h < 8; ++h)
+          if (h < n_rep) acc[h] += sm->s[h][t] * v;
+      }
+    }
+  }
+  {
+    const int d = tid & 63, g = tid >> 6;
+#pragma unroll
+    for (int h = 0; h < 8; ++h)
+      if (h < n_rep) sm->red[g][h][d] = acc[h];
+  }
+  sync();
+  for (int i = tid; i < n_rep * 64; i += kConsumerThreads) {
+    const int h = i >> 6, d = i & 63;
+    const float o = sm->red[0][h][d] + sm->red[1][h][d] + sm->red[2][h][d] + sm->red[3][h][d];
+    const long long hh = static_cast<long long>(b) * p.n_heads + kvh * n_rep + h;
+    p.part_o[(hh * p.max_splits + split) * 64 + d] = o;
+    if (d == 0) {
+      p.part_ml[(hh * p.max_splits + split) * 2 + 0] = sm->ml[h][0];
+      p.part_ml[(hh * p.max_splits + split) * 2 + 1] = sm->ml[h][1];
+    }
+  }
+}
+
+// split geometry shared by the producer of the partials and their consumer
+struct SplitGeom {
+  int n_ctx, npages, pps, nsplit;
+};
+NT_DEVINL SplitGeom split_geom(int seq_len, int max_ctx, int max_splits) {
+  SplitGeom g;
+  g.n_ctx = min(seq_len + 1, max_ctx);
+  g.npages = (g.n_ctx + 63) >> 6;
+  g.pps = (g.npages + max_splits - 1) / max_splits;
+  g.nsplit = (g.npages + g.pps - 1) / g.pps;
+  return g;
+}
+
+// Input staging of the o_proj phase: merge the split partials (in split order) straight into the x planes.
+template <int NB, typename Sync>
+NT_DEVINL void load_attn_merged(const AttnDecParams& p, const int* pos_cache, int split_cap, float4* xs, Sync sync) {
+  const int tid = threadIdx.x;
+  const int HD = p.n_heads * 64, nch = HD >> 3;
+  float* xf = reinterpret_cast<float*>(xs);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const SplitGeom g = split_geom(pos_cache[b], p.kv.max_ctx, split_cap);
+    for (int e = tid; e < HD; e += kConsumerThreads) {
+      const int h = e >> 6, d = e & 63;
+      const long long hh = static_cast<long long>(b) * p.n_heads + h;
+      float M = -INFINITY;
+      for (int s = 0; s < g.nsplit; ++s) M = fmaxf(M, __ldcg(&p.part_ml[(hh * p.max_splits + s) * 2]));
+      float L = 0.f, O = 0.f;
+      for (int s = 0; s < g.nsplit; ++s) {
+        const float w = exp2f(__ldcg(&p.part_ml[(hh * p.max_splits + s) * 2]) - M);
+        L += w * __ldcg(&p.part_ml[(hh * p.max_splits + s) * 2 + 1]);
+        O += w * __ldcg(&p.part_o[(hh * p.max_splits + s) * 64 + d]);
+      }
+      const int m4 = e >> 2;
+      xf[(((2 * b + (m4 & 1)) * nch + (m4 >> 1)) << 2) + (e & 3)] = O / L;
+    }
+  }
+  sync();
+}
+
 // =================================================================================== sampler pieces
 struct Cand {
   float v;
   int i;
 };
 NT_DEVINL bool cand_before(const Cand& a, const Cand& b) { return a.v > b.v || (a.v == b.v && a.i < b.i); }
-
-// full descending bitonic sort of n (power of two) candidates in shared memory
-template <typename Sync>
-NT_DEVINL void bitonic_sort_desc(Cand* a, int n, Sync sync) {
-  const int tid = threadIdx.x;
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (n >> 1); t += kConsumerThreads) {
-        const int i = ((t / j) * 2 * j) + (t % j);
-        const int l = i + j;
-        const bool desc = ((i & k) == 0);
-        const Cand x = a[i], y = a[l];
-        const bool swap = desc ? cand_before(y, x) : cand_before(x, y);
-        if (swap) a[i] = y, a[l] = x;
-      }
-      sync();
-    }
-  }
-}
 
 NT_DEVINL void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -378,38 +507,49 @@ NT_DEVINL void philox4x32_10(uint32_t (&ctr)[4], uint32_t k0, uint32_t k1) {
 
 constexpr int kTopChunk = 2048;
 constexpr int kTopKeep = 64;
+constexpr int kSelList = 512;                       // radix select switches to a compacted list below this size
+constexpr int kSelScratch = 264 + kSelList;         // uint32 words of scratch the selector needs
 
-// order-preserving float -> uint key (larger float <=> larger key; -inf is the smallest finite key)
+// order-preserving float <-> uint key (larger float <=> larger key; -inf is the smallest finite key)
 NT_DEVINL uint32_t f2key(float f) {
   const uint32_t u = __float_as_uint(f);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
+NT_DEVINL float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
 
-// Block-wide radix select (4 passes of 8 bits, MSB first) over n keys in shared memory: finds the
-// key of the k-th largest element and how many elements equal to it belong to the top-k.
-// scratch: >= 258 uint32.
+// Block-wide radix select (4 passes of 8 bits, MSB first) over n keys in shared memory: finds the key
+// of the k-th largest element and how many elements equal to it belong to the top-k.
+//   pass 0 aggregates equal bins inside a warp with match.any (logits crowd into a few top-byte bins);
+//   later passes use plain shared atomics (bins are spread) and, once at most kSelList keys still match
+//   the prefix, run on a compacted list instead of rescanning all n keys.
 template <typename Sync>
 NT_DEVINL void radix_select_kth(const uint32_t* keys, int n, int k, uint32_t* scratch, uint32_t& thr, int& take_eq, Sync sync) {
-  uint32_t* hist = scratch;       // [256]
-  uint32_t* sel = scratch + 256;  // [2]: bin, remaining
+  uint32_t* hist = scratch;        // [256]
+  uint32_t* sel = scratch + 256;   // [0] bin, [1] remaining, [2] count in bin, [3] list length
+  uint32_t* list = scratch + 264;  // [kSelList]
   const int tid = threadIdx.x, lane = tid & 31;
   uint32_t prefix = 0, mask = 0;
   int remaining = k;
-  const int n_pad = (n + 31) & ~31;
+  const uint32_t* src = keys;
+  int ns = n;
 #pragma unroll 1
   for (int pass = 0; pass < 4; ++pass) {
     const int shift = 24 - 8 * pass;
     for (int i = tid; i < 256; i += kConsumerThreads) hist[i] = 0;
+    if (tid == 0) sel[3] = 0;
     sync();
-    for (int i = tid; i < n_pad; i += kConsumerThreads) {
-      uint32_t bin = 0xffffffffu;
-      if (i < n) {
-        const uint32_t key = keys[i];
-        if ((key & mask) == prefix) bin = (key >> shift) & 255u;
+    if (pass == 0) {
+      const int n_pad = (ns + 31) & ~31;
+      for (int i = tid; i < n_pad; i += kConsumerThreads) {
+        const uint32_t bin = (i < ns) ? (src[i] >> 24) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
       }
-      // one shared-memory atomic per distinct bin per warp (logits crowd into few top-byte bins)
-      const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-      if (bin != 0xffffffffu && lane == (__ffs(peers) - 1)) atomicAdd(&hist[bin], __popc(peers));
+    } else {
+      for (int i = tid; i < ns; i += kConsumerThreads) {
+        const uint32_t key = src[i];
+        if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+      }
     }
     sync();
     if (tid < 32) {
@@ -433,6 +573,7 @@ NT_DEVINL void radix_select_kth(const uint32_t* keys, int n, int k, uint32_t* sc
           if (acc + c[j] >= static_cast<uint32_t>(remaining)) {
             sel[0] = 8 * lane + j;
             sel[1] = remaining - acc;
+            sel[2] = c[j];
             break;
           }
           acc += c[j];
@@ -443,7 +584,19 @@ NT_DEVINL void radix_select_kth(const uint32_t* keys, int n, int k, uint32_t* sc
     prefix |= sel[0] << shift;
     mask |= 0xffu << shift;
     remaining = static_cast<int>(sel[1]);
-    sync();
+    const int in_bin = static_cast<int>(sel[2]);
+    if (pass < 3 && src == keys && in_bin <= kSelList) {
+      // compact the keys that still match the prefix; the remaining passes scan only those
+      for (int i = tid; i < ns; i += kConsumerThreads) {
+        const uint32_t key = src[i];
+        if ((key & mask) == prefix) list[atomicAdd(&sel[3], 1u)] = key;
+      }
+      sync();
+      src = list;
+      ns = in_bin;
+    } else {
+      sync();
+    }
   }
   thr = prefix;
   take_eq = remaining;
@@ -491,8 +644,36 @@ NT_DEVINL void compact_topk(const uint32_t* keys, int n, uint32_t thr, int take_
   }
 }
 
-// Sampler stage 1 for one (sequence b, chunk): logits processors + exact top-64 of a 2048-logit chunk.
-// keys: [kTopChunk] uint32 shared; scratch: [260] uint32 shared.
+// Top-kTopKeep of n processed scores already held as keys in shared memory -> candidate slots
+// [o, o + kTopKeep) of the global candidate arrays (processed score, global index = idx_base + i).
+template <typename Sync>
+NT_DEVINL void emit_local_topk(const SamplerParams& p, const uint32_t* keys, int n, int idx_base, long long o, uint32_t* scratch,
+                               Sync sync) {
+  const int tid = threadIdx.x;
+  const int k = min(kTopKeep, n);
+  if (k > 0) {
+    uint32_t thr;
+    int take_eq;
+    radix_select_kth(keys, n, k, scratch, thr, take_eq, sync);
+    compact_topk(keys, n, thr, take_eq, scratch, sync, [&](int slot, int i) {
+      p.cand_val[o + slot] = key2f(keys[i]);
+      p.cand_idx[o + slot] = idx_base + i;
+    });
+  }
+  for (int s = k + tid; s < kTopKeep; s += kConsumerThreads) {
+    p.cand_val[o + s] = -INFINITY;
+    p.cand_idx[o + s] = 0x7fffffff;
+  }
+}
+
+// logits processors (MinNewTokensLength -> Temperature), then the order-preserving key
+NT_DEVINL uint32_t processed_key(float logit, int idx, bool mask_eos, int eos_id, float inv_t) {
+  if (mask_eos && idx == eos_id) logit = -INFINITY;
+  return f2key(logit * inv_t);
+}
+
+// Sampler stage 1 for one (sequence b, chunk): processors + exact top-64 of a 2048-logit chunk read
+// from global memory.  keys: [kTopChunk] uint32 shared; scratch: [kSelScratch] uint32 shared.
 template <typename Sync>
 NT_DEVINL void sample_stage1_chunk(const SamplerParams& p, int b, int chunk, uint32_t* keys, uint32_t* scratch, Sync sync) {
   const int tid = threadIdx.x;
@@ -503,29 +684,13 @@ NT_DEVINL void sample_stage1_chunk(const SamplerParams& p, int b, int chunk, uin
   const int base = chunk * kTopChunk;
   const int n = min(kTopChunk, p.V - base);
   sync();  // keys/scratch may still be in use by the previous call of this CTA
-  for (int e = tid; e < n; e += kConsumerThreads) {
-    float v = __ldcg(lg + base + e);
-    if (mask_eos && base + e == p.sp.eos_id) v = -INFINITY;  // MinNewTokensLength
-    keys[e] = f2key(v * inv_t);                              // Temperature
-  }
+  for (int e = tid; e < n; e += kConsumerThreads) keys[e] = processed_key(__ldcg(lg + base + e), base + e, mask_eos, p.sp.eos_id, inv_t);
   sync();
-  const long long o = (static_cast<long long>(b) * p.nchunks + chunk) * kTopKeep;
-  const int k = min(kTopKeep, n);
-  uint32_t thr;
-  int take_eq;
-  radix_select_kth(keys, n, k, scratch, thr, take_eq, sync);
-  compact_topk(keys, n, thr, take_eq, scratch, sync, [&](int slot, int i) {
-    p.cand_val[o + slot] = __ldcg(lg + base + i);  // raw logit; stage 2 re-applies the processors
-    p.cand_idx[o + slot] = base + i;
-  });
-  for (int s = k + tid; s < kTopKeep; s += kConsumerThreads) {
-    p.cand_val[o + s] = -INFINITY;
-    p.cand_idx[o + s] = 0x7fffffff;
-  }
+  emit_local_topk(p, keys, n, base, (static_cast<long long>(b) * p.nchunks + chunk) * kTopKeep, scratch, sync);
 }
 
-// Sampler stage 2 for sequence b: top-k of the candidates, softmax, draw, state update, next embedding.
-// keys: [ncand] uint32 shared; scratch: [260]; win: [kTopKeep]; s_tok: shared int.
+// Sampler stage 2 for sequence b: top-k of the candidate scores (already processed), softmax, draw,
+// state update, next embedding.  keys: [ncand] uint32 shared; scratch: [kSelScratch]; win: [2*kTopKeep].
 template <typename Sync>
 NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint32_t* keys, uint32_t* scratch, Cand* win, int* s_tok,
                                  Sync sync) {
@@ -533,31 +698,32 @@ NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint3
   const bool stateless = p.n_generated_override != nullptr;
   const int ngen = stateless ? __ldcg(p.n_generated_override + b) : __ldcg(p.n_generated + b);
   const bool is_done = stateless ? false : (__ldcg(p.done + b) != 0);
-  const bool mask_eos = ngen < p.sp.min_new_tokens;
-  const float inv_t = 1.0f / p.sp.temperature;
   const float* cv = p.cand_val + static_cast<long long>(b) * ncand;
   const int32_t* ci = p.cand_idx + static_cast<long long>(b) * ncand;
+  Cand* raw = win + kTopKeep;  // unsorted winners
   sync();
-  for (int e = tid; e < ncand; e += kConsumerThreads) {
-    float v = __ldcg(cv + e);
-    if (mask_eos && __ldcg(ci + e) == p.sp.eos_id) v = -INFINITY;
-    keys[e] = f2key(v * inv_t);
-  }
-  if (tid < kTopKeep) win[tid].v = -INFINITY, win[tid].i = 0x7fffffff;
+  for (int e = tid; e < ncand; e += kConsumerThreads) keys[e] = f2key(__ldcg(cv + e));
+  if (tid < kTopKeep) raw[tid].v = -INFINITY, raw[tid].i = 0x7fffffff;
   sync();
   const int k = min(min(p.sp.top_k, kTopKeep), ncand);
   uint32_t thr;
   int take_eq;
   radix_select_kth(keys, ncand, k, scratch, thr, take_eq, sync);
   compact_topk(keys, ncand, thr, take_eq, scratch, sync, [&](int slot, int i) {
-    float v = __ldcg(cv + i);
-    const int idx = __ldcg(ci + i);
-    if (mask_eos && idx == p.sp.eos_id) v = -INFINITY;
-    win[slot].v = v * inv_t;
-    win[slot].i = idx;
+    raw[slot].v = key2f(keys[i]);
+    raw[slot].i = __ldcg(ci + i);
   });
   sync();
-  bitonic_sort_desc(win, kTopKeep, sync);  // 64 winners: (score desc, index asc)
+  if (tid < kTopKeep) {  // rank sort of the 64 winners: (score desc, index asc), ties of padding by slot
+    const Cand me = raw[tid];
+    int rank = 0;
+    for (int j = 0; j < kTopKeep; ++j) {
+      const Cand o = raw[j];
+      rank += (cand_before(o, me) || (o.v == me.v && o.i == me.i && j < tid)) ? 1 : 0;
+    }
+    win[rank] = me;
+  }
+  sync();
 
   if (tid < 32) {
     // softmax over the k kept scores (TopK processor + softmax, utils.py:2789)

@@ -56,7 +56,6 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
   float* red = reinterpret_cast<float*>(smem + plan.red_off);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + plan.bar_off);
   uint64_t* empty_bar = full_bar + 8;
-  __shared__ float s_scale[4];
   __shared__ float s_part[kConsumerWarps * 4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -113,7 +112,7 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
   }
 
   // ---- consumers: input vector(s) -> shared memory planes (+ fused RMSNorm), then the stages
-  load_x_planes<NB>(p.x, p.ldx, K, p.norm_w, p.eps, xs, s_part, s_scale, SyncConsumers());
+  load_x_planes<NB>(p.x, p.ldx, K, p.norm_w, p.eps, xs, s_part, SyncConsumers());
   for (int it = 0; it < total_stages; ++it) {
     const int s = it % NS;
     const uint32_t ph = (it / NS) & 1;
@@ -175,12 +174,16 @@ int launch_attn_decode(const AttnDecParams& p, int B, cudaStream_t stream) {
 
 // =================================================================================== sampler
 int sampler_nchunks(int V) { return (V + kTopChunk - 1) / kTopChunk; }
-size_t sampler_scratch_floats(int B, int V) { return size_t(B) * sampler_nchunks(V) * kTopKeep; }
+// candidate arrays: [sequence][chunk][64]; the megakernel indexes chunks by CTA (<= 256), the per-op path by 2048-logit chunk
+size_t sampler_scratch_floats(int B, int V) {
+  const int chunks = sampler_nchunks(V) > 256 ? sampler_nchunks(V) : 256;
+  return size_t(B) * chunks * kTopKeep;
+}
 
 // stage 1: grid (nchunks, B), 256 threads
 __global__ void __launch_bounds__(kConsumerThreads) topk_stage1_kernel(const SamplerParams p) {
   __shared__ uint32_t keys[kTopChunk];
-  __shared__ uint32_t scratch[260];
+  __shared__ uint32_t scratch[kSelScratch];
   pdl_launch_dependents();
   pdl_wait();
   sample_stage1_chunk(p, blockIdx.y, blockIdx.x, keys, scratch, SyncAll());
@@ -189,8 +192,8 @@ __global__ void __launch_bounds__(kConsumerThreads) topk_stage1_kernel(const Sam
 // stage 2: grid (B), 256 threads
 __global__ void __launch_bounds__(kConsumerThreads) topk_stage2_kernel(const SamplerParams p, const int ncand) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint32_t scratch[260];
-  __shared__ Cand win[kTopKeep];
+  __shared__ uint32_t scratch[kSelScratch];
+  __shared__ Cand win[2 * kTopKeep];
   __shared__ int s_tok;
   pdl_launch_dependents();
   pdl_wait();

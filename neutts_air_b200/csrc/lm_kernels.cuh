@@ -39,6 +39,12 @@ struct GemvParams {
   KVLayout kv;
   int layer, n_heads;
   const float* inv_freq;   // [32]
+  // optional shared-memory side channels (megakernel; all null/0 in the per-op kernels)
+  const int* pos_cache;    // [nb] this step's seq_lens snapshot
+  const int* page_cache;   // [nb] page id holding the new token
+  const float* bias_smem;  // this CTA's bias slice, indexed by (row - row0)
+  float* smem_out;         // GEMV_STORE: also keep the result at smem_out[b * smem_ld + row - row0]
+  int smem_ld, row0;
 };
 
 int launch_gemv(const GemvParams& p, int nb, int num_sms, cudaStream_t stream);
@@ -48,8 +54,8 @@ struct AttnDecParams {
   KVLayout kv;
   int layer, n_heads, n_rep;
   float scale_log2;  // head_dim^-0.5 * log2(e)
-  float* part_o;     // [B, n_heads, max_splits, 64]
-  float* part_ml;    // [B, n_heads, max_splits, 2]
+  float* part_o;     // [B, n_heads, max_splits, 64]  (unnormalised: sum_t 2^(s_t - m) v_t)
+  float* part_ml;    // [B, n_heads, max_splits, 2]   (m, l) in the log2 domain
   int* counters;     // [B, n_kv_heads]
   float* out;        // [B, n_heads*64]
   __nv_bfloat16* out_bf16;  // optional copy for the tensor-core o_proj

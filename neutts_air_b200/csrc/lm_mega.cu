@@ -16,6 +16,8 @@
 #include "lm_device.cuh"
 #include "lm_mega.cuh"
 
+#include <cstdlib>
+
 namespace nt {
 
 NT_DEVINL unsigned ld_relaxed_gpu(const unsigned* p) {
@@ -85,16 +87,25 @@ NT_DEVINL PhaseSlice phase_slice(const MegaPhase& ph) {
   return s;
 }
 
+NT_DEVINL void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+NT_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+NT_DEVINL void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int NB>
 __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kernel(const MegaParams P) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* ring = smem + P.ring_off;
   float4* xs = reinterpret_cast<float4*>(smem + P.x_off);
-  uint8_t* uni = smem + P.union_off;  // AttnSmem  |  sampler keys + scratch + winners
+  uint8_t* uni = smem + P.union_off;  // AttnSmem | head-phase logits + selector scratch ; x+uni together: final selection
   float* red = reinterpret_cast<float*>(smem + P.misc_off);
   float* s_part = red + 2 * kConsumerWarps * 2 * 4;
-  float* s_scale = s_part + kConsumerWarps * 4;
+  int* pos_cache = reinterpret_cast<int*>(s_part + kConsumerWarps * 4);
+  int* page_cache = pos_cache + 4;
+  float* norm_buf = reinterpret_cast<float*>(page_cache + 4);
+  float* bias_buf = norm_buf + P.hidden;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P.bar_off);
   uint64_t* empty_bar = full_bar + 8;
   AttnSync* async_ = reinterpret_cast<AttnSync*>(empty_bar + 8);
@@ -135,6 +146,29 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
         if (go < 0) break;
         for (int ph = 0; ph < n_phases; ++ph) {
           const int pidx = (ph == n_phases - 1) ? (4 * P.total_layers) : ph;  // lm_head is the last table entry
+          if (P.l2_prefetch && (ph & 3) == 0 && ph < 4 * L) {
+            // entering layer l: pull this CTA's slices of layer l+1 (or the head of the lm_head slice) into L2
+            const int l = ph >> 2;
+            if (l + 1 < L) {
+              for (int q = 0; q < 4; ++q) {
+                const MegaPhase np = P.phases[4 * (l + 1) + q];
+                const PhaseSlice ns = phase_slice(np);
+                if (ns.my_units > 0)
+                  bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(np.W) + static_cast<long long>(ns.u_begin) * ns.unit_bytes,
+                                   static_cast<uint32_t>(ns.my_units) * ns.unit_bytes);
+              }
+            }
+            if (l + 2 >= L) {
+              const MegaPhase hp = P.phases[4 * P.total_layers];
+              const PhaseSlice hs = phase_slice(hp);
+              const long long total = static_cast<long long>(hs.my_units) * hs.unit_bytes;
+              const long long chunk = P.l2_head_bytes / 2;
+              const long long off = (l + 2 == L) ? 0 : chunk;
+              if (off < total)
+                bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(hp.W) + static_cast<long long>(hs.u_begin) * hs.unit_bytes + off,
+                                 static_cast<uint32_t>(min(chunk, total - off)) & ~15u);
+            }
+          }
           const MegaPhase mp = P.phases[pidx];
           const PhaseSlice sl = phase_slice(mp);
           const uint8_t* wbase = reinterpret_cast<const uint8_t*>(mp.W) + static_cast<long long>(sl.u_begin) * sl.unit_bytes;
@@ -155,14 +189,30 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
 
   // ============================================================== consumer warps
   uint32_t g = 0;
-  unsigned target = 0;  // barrier epoch (flags are zeroed before every launch)
+  unsigned target = 0;
   const unsigned G = gridDim.x;
   Prof prof{nullptr, 0};
+  const SyncConsumers csync;
+  const int H = P.hidden, I = P.inter, HD = P.n_heads * 64;
+  const int n_rep = P.n_heads / P.kv.n_kv_heads;
+  const int split_cap = P.split_cap;
 
-  auto gemv_phase = [&](const GemvParams& gp, int pidx) {
-    const MegaPhase mp = P.phases[pidx];
-    const PhaseSlice sl = phase_slice(mp);
-    load_x_planes<NB>(gp.x, gp.ldx, gp.K, gp.norm_w, gp.eps, xs, s_part, s_scale, SyncConsumers());
+  // this CTA's slice of every layer's QKV bias (immutable) -> shared memory, once
+  const PhaseSlice qkv_sl = phase_slice(P.phases[0]);
+  const int bias_rows = 2 * qkv_sl.my_units;
+  const bool bias_cached = bias_rows <= P.bias_cap;
+  if (bias_cached)
+    for (int i = tid; i < L * bias_rows; i += kConsumerThreads) {
+      const int l = i / bias_rows, r = i - l * bias_rows;
+      bias_buf[l * P.bias_cap + r] = __ldg(P.bqkv[l] + 2 * qkv_sl.u_begin + r);
+    }
+
+  auto prefetch_norm = [&](const float* w) {  // asynchronous global -> shared copy of one RMSNorm weight vector
+    if (tid < (H >> 2)) cp_async16(norm_buf + 4 * tid, w + 4 * tid);
+    cp_async_commit();
+  };
+
+  auto run_stages = [&](const GemvParams& gp, const PhaseSlice& sl) {
     if (tid == 0) prof.mark();  // input vector staged
     for (int it = 0; it < sl.stages; ++it, ++g) {
       const int slot = g % NS;
@@ -175,7 +225,14 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     }
   };
 
-  const int H = P.hidden, I = P.inter, HD = P.n_heads * 64;
+  AttnDecParams ap;
+  ap.q = P.q, ap.kv = P.kv, ap.n_heads = P.n_heads, ap.n_rep = n_rep, ap.scale_log2 = P.scale_log2;
+  ap.part_o = P.part_o, ap.part_ml = P.part_ml, ap.counters = P.counters, ap.out = P.attn, ap.out_bf16 = nullptr;
+  ap.max_splits = P.max_splits, ap.layer = 0;
+  // the attention item of this CTA (at most one): (sequence, kv head, split)
+  const int per_b = P.kv.n_kv_heads * split_cap;
+  const int my_b = blockIdx.x / per_b, my_kvh = (blockIdx.x % per_b) / split_cap, my_split = blockIdx.x % split_cap;
+
   for (int step = 0; step < P.n_steps; ++step) {
     if (P.prof && tid == 0 && step == P.prof_step && (blockIdx.x == 0 || blockIdx.x == G - 1)) {
       prof.buf = P.prof + (blockIdx.x == 0 ? 0 : kProfMarks);
@@ -184,56 +241,83 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     } else {
       prof.buf = nullptr;
     }
+    // per-step snapshot of the sequence lengths and of the page that receives the new token
+    if (tid < NB) {
+      const int pos = __ldcg(P.kv.seq_lens + tid);
+      pos_cache[tid] = pos;
+      page_cache[tid] = (pos < P.kv.max_ctx) ? __ldcg(P.kv.page_table + tid * P.kv.max_pages_per_seq + (pos >> 6)) : 0;
+    }
+    prefetch_norm(P.ln1[0]);
+    csync();
+    SplitGeom geo{0, 0, 1, 0};
+    const bool has_item = my_b < NB;
+    if (has_item) geo = split_geom(pos_cache[my_b], P.kv.max_ctx, split_cap);
+    const bool item_live = has_item && my_split < geo.nsplit;
+    const bool can_prefetch_kv = item_live && (my_split * geo.pps < geo.npages - 1);  // first page is not the one being appended to
+
     for (int l = 0; l < L; ++l) {
       GemvParams gp;
       // ---- QKV: fused RMSNorm + bias + RoPE + KV-page append
       gp = GemvParams{};
-      gp.W = P.phases[4 * l + 0].W, gp.rows = P.qkv_n, gp.K = H, gp.x = P.h, gp.ldx = H;
-      gp.norm_w = P.ln1[l], gp.eps = P.eps, gp.bias = P.bqkv[l];
+      gp.rows = P.qkv_n, gp.K = H, gp.eps = P.eps, gp.bias = P.bqkv[l];
       gp.epi = GEMV_QKV_ROPE, gp.q_out = P.q, gp.kv = P.kv, gp.layer = l, gp.n_heads = P.n_heads, gp.inv_freq = P.inv_freq;
-      gemv_phase(gp, 4 * l + 0);
+      gp.pos_cache = pos_cache, gp.page_cache = page_cache;
+      if (bias_cached) gp.bias_smem = bias_buf + l * P.bias_cap, gp.row0 = 2 * qkv_sl.u_begin;
+      cp_async_wait_all();
+      load_x_planes<NB>(P.h, H, H, norm_buf, P.eps, xs, s_part, csync);
+      run_stages(gp, qkv_sl);
+      ap.layer = l;
+      if (can_prefetch_kv && tid == 0) attn_issue_page(ap, my_b, my_kvh, my_split * geo.pps, asmem, async_);
       grid_sync(P.gbar, target, G, prof);
-      // ---- split-KV attention: items (b, kv head, split) round-robin over the CTAs
-      {
-        AttnDecParams ap;
-        ap.q = P.q, ap.kv = P.kv, ap.layer = l, ap.n_heads = P.n_heads, ap.n_rep = P.n_heads / P.kv.n_kv_heads;
-        ap.scale_log2 = P.scale_log2, ap.part_o = P.part_o, ap.part_ml = P.part_ml, ap.counters = P.counters;
-        ap.out = P.attn, ap.out_bf16 = nullptr, ap.max_splits = P.max_splits;
-        const int per_b = P.kv.n_kv_heads * P.max_splits;
-        for (int item = blockIdx.x; item < NB * per_b; item += G) {
-          const int b = item / per_b, r = item - b * per_b;
-          const int kvh = r / P.max_splits, split = r - kvh * P.max_splits;
-          const int n_ctx = min(__ldcg(P.kv.seq_lens + b) + 1, P.kv.max_ctx);
-          const int nsplit = (n_ctx + 63) >> 6;
-          if (split < nsplit) attn_decode_item(ap, b, kvh, split, n_ctx, nsplit, asmem, async_, SyncConsumers());
-        }
-      }
+      // ---- split-KV attention: partial (m, l, o) per split, merged by the consumers of the output
+      if (item_live) attn_split_item(ap, my_b, my_kvh, my_split, geo.pps, geo.npages, geo.n_ctx, asmem, async_, can_prefetch_kv, csync);
+      prefetch_norm(P.ln2[l]);
       grid_sync(P.gbar, target, G, prof);
-      // ---- o_proj + residual
+      // ---- o_proj + residual (input = merged attention output)
       gp = GemvParams{};
-      gp.W = P.phases[4 * l + 1].W, gp.rows = H, gp.K = HD, gp.x = P.attn, gp.ldx = HD;
-      gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
-      gemv_phase(gp, 4 * l + 1);
+      gp.rows = H, gp.K = HD, gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
+      load_attn_merged<NB>(ap, pos_cache, split_cap, xs, csync);
+      run_stages(gp, phase_slice(P.phases[4 * l + 1]));
       grid_sync(P.gbar, target, G, prof);
       // ---- RMSNorm + gate/up + SiLU*up
       gp = GemvParams{};
-      gp.W = P.phases[4 * l + 2].W, gp.rows = 2 * I, gp.K = H, gp.x = P.h, gp.ldx = H;
-      gp.norm_w = P.ln2[l], gp.eps = P.eps, gp.epi = GEMV_SWIGLU, gp.out = P.act, gp.ldo = I;
-      gemv_phase(gp, 4 * l + 2);
+      gp.rows = 2 * I, gp.K = H, gp.eps = P.eps, gp.epi = GEMV_SWIGLU, gp.out = P.act, gp.ldo = I;
+      cp_async_wait_all();
+      load_x_planes<NB>(P.h, H, H, norm_buf, P.eps, xs, s_part, csync);
+      run_stages(gp, phase_slice(P.phases[4 * l + 2]));
+      prefetch_norm(l + 1 < L ? P.ln1[l + 1] : P.final_norm);
       grid_sync(P.gbar, target, G, prof);
       // ---- down + residual
       gp = GemvParams{};
-      gp.W = P.phases[4 * l + 3].W, gp.rows = H, gp.K = I, gp.x = P.act, gp.ldx = I;
-      gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
-      gemv_phase(gp, 4 * l + 3);
+      gp.rows = H, gp.K = I, gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
+      load_x_planes<NB>(P.act, I, I, nullptr, 0.f, xs, s_part, csync);
+      run_stages(gp, phase_slice(P.phases[4 * l + 3]));
       grid_sync(P.gbar, target, G, prof);
     }
-    // ---- lm_head (fused final RMSNorm)
+    // ---- lm_head (fused final RMSNorm); the CTA keeps its own logits in shared memory and selects its
+    //      local top-64 per sequence right away (no second pass over the logits, no extra barrier)
     {
+      const PhaseSlice hs = phase_slice(P.phases[4 * P.total_layers]);
+      float* lsm = reinterpret_cast<float*>(uni);
       GemvParams gp{};
-      gp.W = P.phases[4 * P.total_layers].W, gp.rows = P.vocab, gp.K = H, gp.x = P.h, gp.ldx = H;
-      gp.norm_w = P.final_norm, gp.eps = P.eps, gp.epi = GEMV_STORE, gp.out = P.logits, gp.ldo = P.vocab;
-      gemv_phase(gp, 4 * P.total_layers);
+      gp.rows = P.vocab, gp.K = H, gp.eps = P.eps, gp.epi = GEMV_STORE, gp.out = P.logits, gp.ldo = P.vocab;
+      gp.smem_out = lsm, gp.smem_ld = P.head_ld, gp.row0 = 2 * hs.u_begin;
+      cp_async_wait_all();
+      load_x_planes<NB>(P.h, H, H, norm_buf, P.eps, xs, s_part, csync);
+      run_stages(gp, hs);
+      csync();
+      uint32_t* scratch = reinterpret_cast<uint32_t*>(lsm + NB * P.head_ld);
+      const int n_local = 2 * hs.my_units;
+      const float inv_t = 1.0f / P.samp.sp.temperature;
+#pragma unroll 1
+      for (int b = 0; b < NB; ++b) {
+        const bool mask_eos = __ldcg(P.samp.n_generated + b) < P.samp.sp.min_new_tokens;
+        uint32_t* keys = reinterpret_cast<uint32_t*>(lsm + b * P.head_ld);
+        for (int e = tid; e < n_local; e += kConsumerThreads)
+          keys[e] = processed_key(lsm[b * P.head_ld + e], gp.row0 + e, mask_eos, P.samp.sp.eos_id, inv_t);
+        csync();
+        emit_local_topk(P.samp, keys, n_local, gp.row0, (static_cast<long long>(b) * G + blockIdx.x) * kTopKeep, scratch, csync);
+      }
     }
     grid_sync(P.gbar, target, G, prof);
     if (P.logits_out) {  // tests: keep every step's logits
@@ -242,21 +326,14 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       for (long long i = static_cast<long long>(blockIdx.x) * kConsumerThreads + tid; i < n; i += static_cast<long long>(G) * kConsumerThreads)
         dst[i] = __ldcg(P.logits + i);
     }
-    // ---- sampler stage 1: per-chunk top-64 (radix select), chunks round-robin over the CTAs
-    {
-      uint32_t* keys = reinterpret_cast<uint32_t*>(uni);
-      uint32_t* scratch = keys + P.samp_keys;
-      for (int item = blockIdx.x; item < NB * P.samp.nchunks; item += G)
-        sample_stage1_chunk(P.samp, item / P.samp.nchunks, item % P.samp.nchunks, keys, scratch, SyncConsumers());
-    }
-    grid_sync(P.gbar, target, G, prof);
-    // ---- sampler stage 2: CTA b finishes sequence b (top-k, softmax, draw, state, next embedding)
+    // ---- final selection: CTA b finishes sequence b (top-k over G*64 candidates, softmax, draw, state, next embedding)
     if (static_cast<int>(blockIdx.x) < NB) {
-      uint32_t* keys = reinterpret_cast<uint32_t*>(uni);
-      uint32_t* scratch = keys + P.samp_keys;
-      Cand* win = reinterpret_cast<Cand*>(scratch + 260);
-      int* s_tok = reinterpret_cast<int*>(win + kTopKeep);
-      sample_stage2_seq(P.samp, blockIdx.x, P.samp.nchunks * kTopKeep, keys, scratch, win, s_tok, SyncConsumers());
+      const int ncand = static_cast<int>(G) * kTopKeep;
+      uint32_t* keys = reinterpret_cast<uint32_t*>(xs);  // x planes + union region are contiguous and idle here
+      uint32_t* scratch = keys + ncand;
+      Cand* win = reinterpret_cast<Cand*>(scratch + kSelScratch);
+      int* s_tok = reinterpret_cast<int*>(win + 2 * kTopKeep);
+      sample_stage2_seq(P.samp, blockIdx.x, ncand, keys, scratch, win, s_tok, csync);
     }
     grid_sync(P.gbar, target, G, prof);
     // ---- stop when every sequence is finished (same decision in every CTA: flags were published before the barrier)
@@ -265,42 +342,57 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     if (all_done || step + 1 == P.n_steps) break;
     if (tid == 0) *s_go = step + 2;  // release the producer into the next step
   }
+  cp_async_wait_all();
   asm volatile("bar.sync 1, 256;" ::: "memory");
   if (tid == 0) *s_go = -1;
 }
 
 int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream) {
   if (nb < 1 || nb > 4) return set_error(NT_ERR_INVALID, "megakernel: batch %d not in 1..4", nb);
-  if (num_sms > 256) num_sms = 256;  // size of the barrier flag array
-  // shared-memory plan
-  const int k_small = P.hidden, k_big = P.inter > P.n_heads * 64 ? P.inter : P.n_heads * 64;
+  if (num_sms > 256) num_sms = 256;
+  // ---- shared-memory plan
+  const int HD = P.n_heads * 64;
+  const int k_small = P.hidden, k_big = P.inter > HD ? P.inter : HD;
   auto unit_stage = [](int K) { return (K >= 2048 ? 1 : kConsumerWarps) * 4 * K; };
-  int stage = unit_stage(k_small);
-  if (unit_stage(k_big) > stage) stage = unit_stage(k_big);
-  if (unit_stage(P.n_heads * 64) > stage) stage = unit_stage(P.n_heads * 64);
+  int stage = unit_stage(P.hidden);
+  if (unit_stage(P.inter) > stage) stage = unit_stage(P.inter);
+  if (unit_stage(HD) > stage) stage = unit_stage(HD);
   stage = (stage + 127) & ~127;
-  const size_t x_bytes = size_t(nb) * (k_big > k_small ? k_big : k_small) * 4;
-  const int ncand = P.samp.nchunks * kTopKeep;
-  P.samp_keys = ncand > kTopChunk ? ncand : kTopChunk;
-  size_t uni = size_t(P.samp_keys) * 4 + 260 * 4 + kTopKeep * sizeof(Cand) + 16;
+  const size_t x_bytes = (size_t(nb) * (k_big > k_small ? k_big : k_small) * 4 + 127) & ~size_t(127);
+  // union region: attention staging | head-phase logits (nb rows) + selector scratch
+  P.head_ld = 2 * ((P.vocab / 2 + num_sms - 1) / num_sms) + 8;
+  size_t uni = size_t(nb) * P.head_ld * 4 + kSelScratch * 4 + 64;
   if (sizeof(AttnSmem) > uni) uni = sizeof(AttnSmem);
   uni = (uni + 127) & ~size_t(127);
-  const size_t misc = (2 * kConsumerWarps * 2 * 4 + kConsumerWarps * 4 + 4) * sizeof(float);
-  const size_t bars = 16 * sizeof(uint64_t) + sizeof(AttnSync) + 16;
-  const size_t fixed = ((x_bytes + 127) & ~size_t(127)) + uni + ((misc + 127) & ~size_t(127)) + bars + 128;
+  // the final selection needs G*64 keys + scratch + winners inside x + union
+  const size_t final_need = size_t(num_sms) * kTopKeep * 4 + kSelScratch * 4 + 2 * kTopKeep * sizeof(Cand) + 64;
+  if (x_bytes + uni < final_need) uni = ((final_need - x_bytes) + 127) & ~size_t(127);
+  const int qkv_units = P.qkv_n / 2;
+  P.bias_cap = 2 * ((qkv_units + num_sms - 1) / num_sms) + 2;
+  if (P.bias_cap > 64) P.bias_cap = 0;  // huge slices: read the bias from global memory instead
+  const size_t misc = ((2 * kConsumerWarps * 2 * 4 + kConsumerWarps * 4) * sizeof(float) + 8 * sizeof(int) + size_t(P.hidden) * 4 +
+                       size_t(P.total_layers) * P.bias_cap * 4 + 127) & ~size_t(127);
+  const size_t bars = (16 * sizeof(uint64_t) + sizeof(AttnSync) + 16 + 127) & ~size_t(127);
+  const size_t fixed = x_bytes + uni + misc + bars + 128;
   const size_t budget = 227 * 1024;
   if (fixed + 2 * size_t(stage) > budget) return set_error(NT_ERR_INVALID, "megakernel: model does not fit the shared-memory plan");
   int ns = int((budget - fixed) / stage);
   if (ns > 8) ns = 8;
   P.nstages = ns;
   P.stage_bytes = stage;
+  P.split_cap = 16 / nb > 0 ? 16 / nb : 1;
+  if (P.split_cap > P.max_splits) P.split_cap = P.max_splits;
+  if (nb * P.kv.n_kv_heads * P.split_cap > num_sms) return set_error(NT_ERR_INVALID, "megakernel: too few SMs for the attention items");
+  P.l2_prefetch = getenv("NT_NO_L2_PREFETCH") ? 0 : 1;
+  P.l2_head_bytes = 256 * 1024;
   size_t off = 0;
   P.ring_off = off, off += size_t(ns) * stage;
-  P.x_off = off, off += (x_bytes + 127) & ~size_t(127);
+  P.x_off = off, off += x_bytes;
   P.union_off = off, off += uni;
-  P.misc_off = off, off += (misc + 127) & ~size_t(127);
+  P.misc_off = off, off += misc;
   P.bar_off = off, off += bars;
   const size_t smem = off + 128;
+  P.samp.nchunks = num_sms;  // candidate arrays are indexed [sequence][CTA][64] in this path
 
   void (*kern)(const MegaParams) = nullptr;
   switch (nb) {

@@ -33,8 +33,13 @@ struct MegaParams {
   float* logits_out;  // optional [n_steps][nb][vocab]
   long long* prof;    // optional timeline buffer [2 CTAs][kProfMarks] of %globaltimer ns (profiles/probe_mega.py)
   int prof_step;
-  // shared-memory plan (filled by launch_decode_mega)
-  int nstages, stage_bytes, samp_keys;
+  // shared-memory plan and tuning (filled by launch_decode_mega)
+  int nstages, stage_bytes;
+  int head_ld;        // row length of the per-CTA logits copy kept in shared memory during the lm_head phase
+  int bias_cap;       // per-layer slots of the cached QKV bias slice (0 = not cached)
+  int split_cap;      // attention splits per (sequence, kv head): 16 / batch
+  int l2_prefetch;    // producer prefetches the next layer's slices into L2
+  long long l2_head_bytes;
   size_t ring_off, x_off, union_off, misc_off, bar_off;
 };
 

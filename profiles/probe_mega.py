@@ -31,7 +31,7 @@ for c in range(2):
         names += [f"L{l}.qkv.x", f"L{l}.qkv.done", f"L{l}.qkv.arr", f"L{l}.qkv.rel", f"L{l}.att.done", f"L{l}.att.arr", f"L{l}.att.rel"]
         for ph in ("o", "gu", "d"):
             names += [f"L{l}.{ph}.x", f"L{l}.{ph}.done", f"L{l}.{ph}.arr", f"L{l}.{ph}.rel"]
-    names += ["head.x", "head.done", "head.arr", "head.rel", "s1.done", "s1.arr", "s1.rel", "s2.done", "s2.arr", "s2.rel"]
+    names += ["head.x", "head.done(+local topk)", "head.arr", "head.rel", "final.done", "final.arr", "final.rel"]
     agg = {}
     for nme, dt in zip(names, d):
         key = nme.split(".", 1)[1] if nme.startswith("L") else nme
