@@ -38,10 +38,21 @@ NT_DEVINL void load_x_planes(const float* x, long long ldx, int K, const float* 
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     const float4* src = reinterpret_cast<const float4*>(x + b * ldx);
-    for (int m = tid; m < nvec; m += kConsumerThreads) {
-      const float4 v = __ldcg(src + m);
-      xs[(2 * b + (m & 1)) * nch + (m >> 1)] = v;
-      ssq[b] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    for (int m0 = 0; m0 < nvec; m0 += 4 * kConsumerThreads) {  // 4 independent loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m0 + j * kConsumerThreads + tid;
+        v[j] = (m < nvec) ? __ldcg(src + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = m0 + j * kConsumerThreads + tid;
+        if (m < nvec) {
+          xs[(2 * b + (m & 1)) * nch + (m >> 1)] = v[j];
+          ssq[b] += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+        }
+      }
     }
   }
   if (norm_w) {
@@ -460,27 +471,52 @@ NT_DEVINL SplitGeom split_geom(int seq_len, int max_ctx, int max_splits) {
 }
 
 // Input staging of the o_proj phase: merge the split partials (in split order) straight into the x planes.
+// Two round trips to L2 in total: (1) all (m, l) pairs of the batch -> shared memory, turned into
+// per-split weights w_s = 2^(m_s - M) / L;  (2) every output element gathers its <= 16 partial values with
+// independent loads.  wbuf: shared float [NB * n_heads * 16].
 template <int NB, typename Sync>
-NT_DEVINL void load_attn_merged(const AttnDecParams& p, const int* pos_cache, int split_cap, float4* xs, Sync sync) {
+NT_DEVINL void load_attn_merged(const AttnDecParams& p, const int* pos_cache, int split_cap, float4* xs, float* wbuf, Sync sync) {
   const int tid = threadIdx.x;
   const int HD = p.n_heads * 64, nch = HD >> 3;
   float* xf = reinterpret_cast<float*>(xs);
+  // (1) one thread per (sequence, head): read its nsplit (m, l) pairs, write normalised weights
+  for (int i = tid; i < NB * p.n_heads; i += kConsumerThreads) {
+    const int b = i / p.n_heads;
+    const SplitGeom g = split_geom(pos_cache[b], p.kv.max_ctx, split_cap);
+    const float2* ml = reinterpret_cast<const float2*>(p.part_ml) + static_cast<long long>(i) * p.max_splits;
+    float2 v[16];
+#pragma unroll
+    for (int s = 0; s < 16; ++s) v[s] = (s < g.nsplit) ? __ldcg(ml + s) : make_float2(-INFINITY, 0.f);
+    float M = -INFINITY;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) M = fmaxf(M, v[s].x);
+    float L = 0.f;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      v[s].x = exp2f(v[s].x - M);  // exactly 0 for the unused slots
+      L += v[s].x * v[s].y;
+    }
+    const float inv = 1.0f / L;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) wbuf[i * 16 + s] = v[s].x * inv;
+  }
+  sync();
+  // (2) gather
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     const SplitGeom g = split_geom(pos_cache[b], p.kv.max_ctx, split_cap);
     for (int e = tid; e < HD; e += kConsumerThreads) {
       const int h = e >> 6, d = e & 63;
       const long long hh = static_cast<long long>(b) * p.n_heads + h;
-      float M = -INFINITY;
-      for (int s = 0; s < g.nsplit; ++s) M = fmaxf(M, __ldcg(&p.part_ml[(hh * p.max_splits + s) * 2]));
-      float L = 0.f, O = 0.f;
-      for (int s = 0; s < g.nsplit; ++s) {
-        const float w = exp2f(__ldcg(&p.part_ml[(hh * p.max_splits + s) * 2]) - M);
-        L += w * __ldcg(&p.part_ml[(hh * p.max_splits + s) * 2 + 1]);
-        O += w * __ldcg(&p.part_o[(hh * p.max_splits + s) * 64 + d]);
-      }
+      const float* po = p.part_o + hh * p.max_splits * 64 + d;
+      float o[16];
+#pragma unroll
+      for (int s = 0; s < 16; ++s) o[s] = (s < g.nsplit) ? __ldcg(po + s * 64) : 0.f;
+      float acc = 0.f;
+#pragma unroll
+      for (int s = 0; s < 16; ++s) acc += wbuf[hh * 16 + s] * o[s];
       const int m4 = e >> 2;
-      xf[(((2 * b + (m4 & 1)) * nch + (m4 >> 1)) << 2) + (e & 3)] = O / L;
+      xf[(((2 * b + (m4 & 1)) * nch + (m4 >> 1)) << 2) + (e & 3)] = acc;
     }
   }
   sync();
@@ -587,9 +623,17 @@ NT_DEVINL void radix_select_kth(const uint32_t* keys, int n, int k, uint32_t* sc
     const int in_bin = static_cast<int>(sel[2]);
     if (pass < 3 && src == keys && in_bin <= kSelList) {
       // compact the keys that still match the prefix; the remaining passes scan only those
-      for (int i = tid; i < ns; i += kConsumerThreads) {
-        const uint32_t key = src[i];
-        if ((key & mask) == prefix) list[atomicAdd(&sel[3], 1u)] = key;
+      const int ns_pad = (ns + 31) & ~31;
+      for (int i = tid; i < ns_pad; i += kConsumerThreads) {  // warp-aggregated append: one shared atomic per warp and round
+        const uint32_t key = (i < ns) ? src[i] : 0u;
+        const bool hit = (i < ns) && ((key & mask) == prefix);
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&sel[3], static_cast<uint32_t>(__popc(m)));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (hit) list[base + __popc(m & ((1u << lane) - 1u))] = key;
+        }
       }
       sync();
       src = list;
@@ -684,16 +728,31 @@ NT_DEVINL void sample_stage1_chunk(const SamplerParams& p, int b, int chunk, uin
   const int base = chunk * kTopChunk;
   const int n = min(kTopChunk, p.V - base);
   sync();  // keys/scratch may still be in use by the previous call of this CTA
-  for (int e = tid; e < n; e += kConsumerThreads) keys[e] = processed_key(__ldcg(lg + base + e), base + e, mask_eos, p.sp.eos_id, inv_t);
+  {
+    float v[kTopChunk / kConsumerThreads];
+#pragma unroll
+    for (int j = 0; j < kTopChunk / kConsumerThreads; ++j) {
+      const int e = j * kConsumerThreads + tid;
+      v[j] = (e < n) ? __ldcg(lg + base + e) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kTopChunk / kConsumerThreads; ++j) {
+      const int e = j * kConsumerThreads + tid;
+      if (e < n) keys[e] = processed_key(v[j], base + e, mask_eos, p.sp.eos_id, inv_t);
+    }
+  }
   sync();
   emit_local_topk(p, keys, n, base, (static_cast<long long>(b) * p.nchunks + chunk) * kTopKeep, scratch, sync);
 }
 
 // Sampler stage 2 for sequence b: top-k of the candidate scores (already processed), softmax, draw,
 // state update, next embedding.  keys: [ncand] uint32 shared; scratch: [kSelScratch]; win: [2*kTopKeep].
-template <typename Sync>
+struct NoMark {
+  NT_DEVINL void operator()() const {}
+};
+template <typename Sync, typename Mark = NoMark>
 NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint32_t* keys, uint32_t* scratch, Cand* win, int* s_tok,
-                                 Sync sync) {
+                                 Sync sync, Mark mark = Mark()) {
   const int tid = threadIdx.x;
   const bool stateless = p.n_generated_override != nullptr;
   const int ngen = stateless ? __ldcg(p.n_generated_override + b) : __ldcg(p.n_generated + b);
@@ -702,18 +761,33 @@ NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint3
   const int32_t* ci = p.cand_idx + static_cast<long long>(b) * ncand;
   Cand* raw = win + kTopKeep;  // unsorted winners
   sync();
-  for (int e = tid; e < ncand; e += kConsumerThreads) keys[e] = f2key(__ldcg(cv + e));
+  for (int e0 = 0; e0 < ncand; e0 += 8 * kConsumerThreads) {  // 8 independent loads in flight per thread
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = e0 + j * kConsumerThreads + tid;
+      v[j] = (e < ncand) ? __ldcg(cv + e) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int e = e0 + j * kConsumerThreads + tid;
+      if (e < ncand) keys[e] = f2key(v[j]);
+    }
+  }
   if (tid < kTopKeep) raw[tid].v = -INFINITY, raw[tid].i = 0x7fffffff;
   sync();
+  mark();  // keys staged
   const int k = min(min(p.sp.top_k, kTopKeep), ncand);
   uint32_t thr;
   int take_eq;
   radix_select_kth(keys, ncand, k, scratch, thr, take_eq, sync);
+  mark();  // threshold found
   compact_topk(keys, ncand, thr, take_eq, scratch, sync, [&](int slot, int i) {
     raw[slot].v = key2f(keys[i]);
     raw[slot].i = __ldcg(ci + i);
   });
   sync();
+  mark();  // winners gathered
   if (tid < kTopKeep) {  // rank sort of the 64 winners: (score desc, index asc), ties of padding by slot
     const Cand me = raw[tid];
     int rank = 0;
@@ -724,6 +798,7 @@ NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint3
     win[rank] = me;
   }
   sync();
+  mark();  // winners sorted
 
   if (tid < 32) {
     // softmax over the k kept scores (TopK processor + softmax, utils.py:2789)

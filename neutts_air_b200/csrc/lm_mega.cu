@@ -217,6 +217,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     for (int it = 0; it < sl.stages; ++it, ++g) {
       const int slot = g % NS;
       mbar_wait(&full_bar[slot], (g / NS) & 1);
+      if (tid == 0 && (it == 0 || it == sl.stages - 1)) prof.mark();  // first / last stage of the phase has landed
       const int first = it * sl.ups;
       gemv_consume_stage<NB>(gp, ring + static_cast<size_t>(slot) * P.stage_bytes, xs, red, sl.ups == 1 ? kConsumerWarps : 1, first,
                              min(sl.ups, sl.my_units - first), sl.u_begin, it & 1, [&]() {
@@ -270,13 +271,13 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       if (can_prefetch_kv && tid == 0) attn_issue_page(ap, my_b, my_kvh, my_split * geo.pps, asmem, async_);
       grid_sync(P.gbar, target, G, prof);
       // ---- split-KV attention: partial (m, l, o) per split, merged by the consumers of the output
+      prefetch_norm(P.ln2[l]);  // lands long before the barrier's release fence
       if (item_live) attn_split_item(ap, my_b, my_kvh, my_split, geo.pps, geo.npages, geo.n_ctx, asmem, async_, can_prefetch_kv, csync);
-      prefetch_norm(P.ln2[l]);
       grid_sync(P.gbar, target, G, prof);
       // ---- o_proj + residual (input = merged attention output)
       gp = GemvParams{};
       gp.rows = H, gp.K = HD, gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
-      load_attn_merged<NB>(ap, pos_cache, split_cap, xs, csync);
+      load_attn_merged<NB>(ap, pos_cache, split_cap, xs, reinterpret_cast<float*>(uni), csync);
       run_stages(gp, phase_slice(P.phases[4 * l + 1]));
       grid_sync(P.gbar, target, G, prof);
       // ---- RMSNorm + gate/up + SiLU*up
@@ -284,8 +285,8 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       gp.rows = 2 * I, gp.K = H, gp.eps = P.eps, gp.epi = GEMV_SWIGLU, gp.out = P.act, gp.ldo = I;
       cp_async_wait_all();
       load_x_planes<NB>(P.h, H, H, norm_buf, P.eps, xs, s_part, csync);
+      prefetch_norm(l + 1 < L ? P.ln1[l + 1] : P.final_norm);  // norm_buf is free again: every thread passed the staging barrier
       run_stages(gp, phase_slice(P.phases[4 * l + 2]));
-      prefetch_norm(l + 1 < L ? P.ln1[l + 1] : P.final_norm);
       grid_sync(P.gbar, target, G, prof);
       // ---- down + residual
       gp = GemvParams{};
@@ -333,7 +334,9 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       uint32_t* scratch = keys + ncand;
       Cand* win = reinterpret_cast<Cand*>(scratch + kSelScratch);
       int* s_tok = reinterpret_cast<int*>(win + 2 * kTopKeep);
-      sample_stage2_seq(P.samp, blockIdx.x, ncand, keys, scratch, win, s_tok, csync);
+      sample_stage2_seq(P.samp, blockIdx.x, ncand, keys, scratch, win, s_tok, csync, [&]() {
+        if (tid == 0) prof.mark();
+      });
     }
     grid_sync(P.gbar, target, G, prof);
     // ---- stop when every sequence is finished (same decision in every CTA: flags were published before the barrier)

@@ -27,11 +27,18 @@ for c in range(2):
     # layout: mark0 = step start; per layer: (x, done, arr, rel) qkv | (done, arr, rel) attn | (x,done,arr,rel) o | gu | d
     i = 1
     names = []
+    # marks per GEMV phase: x staged, first stage landed, (last stage landed if > 1 stage), CTA done, arrival published, released
+    nst = {"qkv": 1, "o": 1, "gu": 5, "d": 3, "head": 92}
+    def gemv(prefix, ph):
+        out = [f"{prefix}{ph}.x", f"{prefix}{ph}.w0"]
+        if nst[ph] > 1:
+            out.append(f"{prefix}{ph}.wN")
+        return out + [f"{prefix}{ph}.done", f"{prefix}{ph}.arr", f"{prefix}{ph}.rel"]
     for l in range(layers):
-        names += [f"L{l}.qkv.x", f"L{l}.qkv.done", f"L{l}.qkv.arr", f"L{l}.qkv.rel", f"L{l}.att.done", f"L{l}.att.arr", f"L{l}.att.rel"]
+        names += gemv(f"L{l}.", "qkv") + [f"L{l}.att.done", f"L{l}.att.arr", f"L{l}.att.rel"]
         for ph in ("o", "gu", "d"):
-            names += [f"L{l}.{ph}.x", f"L{l}.{ph}.done", f"L{l}.{ph}.arr", f"L{l}.{ph}.rel"]
-    names += ["head.x", "head.done(+local topk)", "head.arr", "head.rel", "final.done", "final.arr", "final.rel"]
+            names += gemv(f"L{l}.", ph)
+    names += gemv("", "head") + ["final.keys", "final.select", "final.gather", "final.sort", "final.done", "final.arr", "final.rel"]
     agg = {}
     for nme, dt in zip(names, d):
         key = nme.split(".", 1)[1] if nme.startswith("L") else nme
