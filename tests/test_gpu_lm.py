@@ -103,13 +103,16 @@ def test_lm_ragged_batch_prefill_and_decode(cuda, mega, monkeypatch):
         assert rel_err(got[b], mir) < 6e-3 and max_err(got[b], mir) < 5e-2 * float(mir.std()), (b, rel_err(got[b], mir))
 
 
-def test_lm_batched_tensor_core_decode(cuda):
-    """batch 6 (> 4) decodes through the tcgen05 GEMM path with M = batch."""
-    cfg, w, lm = _setup(SMALL, 31, max_batch=8, max_ctx=256)
+@pytest.mark.parametrize("B", [6, 10], ids=["megakernel-bf16-acts", "per-op-tcgen05"])
+def test_lm_batched_decode(cuda, B):
+    """batch 5..8 runs in the megakernel with single-bf16 activations; batch > 8 decodes through the
+    per-op tcgen05 GEMM path with M = batch.  Both round GEMM inputs to bf16, so they are held to the
+    pure-reference bar."""
+    cfg, w, lm = _setup(SMALL, 31, max_batch=16, max_ctx=256)
     g = torch.Generator().manual_seed(2)
-    lens, n_new, eos = [20, 41, 64, 65, 9, 30], 4, cfg.vocab_size - 1
+    lens, n_new, eos = [20, 41, 64, 65, 9, 30, 17, 80, 33, 5][:B], 4, cfg.vocab_size - 1
     prompts = [torch.randint(0, cfg.vocab_size, (n,), generator=g) for n in lens]
-    forced = torch.randint(0, cfg.vocab_size, (6, n_new), generator=g)
+    forced = torch.randint(0, cfg.vocab_size, (B, n_new), generator=g)
     got = _teacher_forced(cfg, w, lm, [p.tolist() for p in prompts], forced, n_new, eos)
     for b, p in enumerate(prompts):
         _, ref = O.generate(cfg, w, p, eos, max_length=256, max_new_tokens=n_new, forced=forced[b], mirror=False)
