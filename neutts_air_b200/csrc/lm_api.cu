@@ -438,7 +438,7 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
   if (n_steps < 0) return set_error(NT_ERR_INVALID, "negative step count");
 
   if (n_steps == 0) return NT_OK;
-  if (!env_flag("NT_NO_MEGA") && mega_supported(c.hidden, c.inter, c.n_heads, B)) {
+  if (B <= 4 && !env_flag("NT_NO_MEGA") && c.hidden % 64 == 0) {
     // persistent megakernel: every layer, the lm_head, the sampler and all n_steps in one launch
     MegaParams P;
     memset(&P, 0, sizeof(P));

@@ -101,9 +101,15 @@ NT_DEVINL void unit_dot(const uint4* r0, const uint4* r1, const float4* xs, int 
   }
 }
 
-// Epilogue of one unit (weight rows 2u, 2u+1) for batch row b: bias, then residual store / SiLU(gate)*up /
-// RoPE + KV-page append.
-NT_DEVINL void unit_epilogue(const GemvParams& p, int u, int b, float a0, float a1) {
+// Epilogue of one unit (rows 2u, 2u+1).  All lanes hold the full sums; lane b finishes batch row b.
+template <int NB>
+NT_DEVINL void gemv_epilogue(const GemvParams& p, int u, float (&d0)[NB], float (&d1)[NB], int lane) {
+  if (lane >= NB) return;
+  const int b = lane;
+  float a0 = d0[0], a1 = d1[0];
+#pragma unroll
+  for (int i = 1; i < NB; ++i)
+    if (b == i) a0 = d0[i], a1 = d1[i];
   const int r0 = 2 * u;
   if (p.bias_smem) {
     a0 += p.bias_smem[r0 - p.row0];
@@ -152,17 +158,6 @@ NT_DEVINL void unit_epilogue(const GemvParams& p, int u, int b, float a0, float 
       *reinterpret_cast<__nv_bfloat162*>(vp + 2 * i) = __floats2bfloat162_rn(a0, a1);
     }
   }
-}
-
-// FMA path: all lanes hold the full sums of the unit; lane b finishes batch row b.
-template <int NB>
-NT_DEVINL void gemv_epilogue(const GemvParams& p, int u, float (&d0)[NB], float (&d1)[NB], int lane) {
-  if (lane >= NB) return;
-  float a0 = d0[0], a1 = d1[0];
-#pragma unroll
-  for (int i = 1; i < NB; ++i)
-    if (lane == i) a0 = d0[i], a1 = d1[i];
-  unit_epilogue(p, u, lane, a0, a1);
 }
 
 // One ring stage of a GEMV phase, executed by the 8 consumer warps.
@@ -226,157 +221,6 @@ NT_DEVINL void gemv_consume_stage(const GemvParams& p, const uint8_t* st, const 
         d0[b] = t0, d1[b] = t1;
       }
       gemv_epilogue<NB>(p, u_begin + first_unit_local, d0, d1, lane);
-    }
-  }
-}
-
-// =================================================================================== tensor-core GEMV (megakernel)
-// The decode GEMVs as mma.sync m16n8k16 (bf16 x bf16 -> fp32): M = batch rows (<= 8 real, rest zero),
-// N = 8 weight rows (one tile = 4 units), K = the hidden dimension.  The activation vector is staged as
-// bf16 hi + lo parts (x = hi + lo to ~2^-17) so the result keeps fp32-level accuracy for batch <= 4;
-// batch 5..8 uses hi only.  Weight rows land in shared memory with a 16-byte row pad (row stride ==
-// 16 mod 128), which makes every ldmatrix conflict-free without touching the global weight layout.
-NT_DEVINL void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
-}
-NT_DEVINL void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
-}
-NT_DEVINL void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
-  // rows 8..15 of A (a1, a3) are the zero padding of the batch dimension
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
-}
-
-// geometry of one weight matrix inside the ring: row blocks of `rps` rows x K chunks of `kc` columns
-struct TileGeom {
-  int r_begin, r_end;  // this CTA's rows
-  int nkc, kc;         // K chunks per row block, columns per chunk
-  int rps;             // rows per stage: 16 (single chunk) or 8
-  int nrb, stages;
-};
-NT_DEVINL TileGeom tile_geom(int rows, int K) {
-  TileGeom t;
-  const int nunits = rows >> 1;
-  t.r_begin = 2 * static_cast<int>((static_cast<long long>(nunits) * blockIdx.x) / gridDim.x);
-  t.r_end = 2 * static_cast<int>((static_cast<long long>(nunits) * (blockIdx.x + 1)) / gridDim.x);
-  t.nkc = (K <= 1024) ? 1 : (K + 1535) / 1536;
-  t.kc = K / t.nkc;  // host checks K % (32 * nkc) == 0
-  t.rps = (t.nkc == 1) ? 16 : 8;
-  t.nrb = (t.r_end - t.r_begin + t.rps - 1) / t.rps;
-  t.stages = t.nrb * t.nkc;
-  return t;
-}
-
-// Activation staging for the tensor-core path: xs[part][b][K + 8] bf16 (part 0 = hi, 1 = lo), fused RMSNorm.
-template <int NB, typename Sync>
-NT_DEVINL void stage_x_bf16(const float* x, long long ldx, int K, const float* norm_w /*global or shared*/, float eps,
-                            __nv_bfloat16* xs, float* s_part, Sync sync) {
-  constexpr bool kLo = NB <= 4;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nvec = K >> 2, xstride = K + 8;
-  float* raw = reinterpret_cast<float*>(xs + (kLo ? 2 : 1) * NB * xstride);  // fp32 scratch behind the bf16 rows (norm only)
-  float ssq[NB];
-#pragma unroll
-  for (int b = 0; b < NB; ++b) ssq[b] = 0.f;
-  auto put = [&](int b, int m, const float4& v) {
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
-    uint2 hv = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-    *reinterpret_cast<uint2*>(xs + b * xstride + 4 * m) = hv;
-    if (kLo) {
-      const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-      __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - f0.x, v.y - f0.y), l1 = __floats2bfloat162_rn(v.z - f1.x, v.w - f1.y);
-      *reinterpret_cast<uint2*>(xs + (NB + b) * xstride + 4 * m) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
-    }
-  };
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    const float4* src = reinterpret_cast<const float4*>(x + b * ldx);
-    for (int m0 = 0; m0 < nvec; m0 += 4 * kConsumerThreads) {
-      float4 v[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int m = m0 + j * kConsumerThreads + tid;
-        v[j] = (m < nvec) ? __ldcg(src + m) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int m = m0 + j * kConsumerThreads + tid;
-        if (m < nvec) {
-          if (norm_w) {
-            reinterpret_cast<float4*>(raw)[b * nvec + m] = v[j];
-            ssq[b] += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
-          } else {
-            put(b, m, v[j]);
-          }
-        }
-      }
-    }
-  }
-  if (norm_w) {
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const float t = warp_sum(ssq[b]);
-      if (lane == 0) s_part[warp * 8 + b] = t;  // s_part: [8 warps][8 batch rows]
-    }
-    sync();
-    const float4* nw = reinterpret_cast<const float4*>(norm_w);
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kConsumerWarps; ++w) t += s_part[w * 8 + b];
-      const float sc = rsqrtf(t / static_cast<float>(K) + eps);
-      for (int m = tid; m < nvec; m += kConsumerThreads) {
-        float4 v = reinterpret_cast<float4*>(raw)[b * nvec + m];  // written by this very thread
-        const float4 g = nw[m];
-        v.x = v.x * sc * g.x, v.y = v.y * sc * g.y, v.z = v.z * sc * g.z, v.w = v.w * sc * g.w;
-        put(b, m, v);
-      }
-    }
-  }
-  sync();
-}
-
-// One ring stage on the tensor cores.  The 8 warps split the K range of the stage; each warp accumulates
-// into acc[tile][4] (carried across the K chunks of a row block).
-//   st        shared address of the stage: rows at stride (kc*2 + 16) bytes
-//   xs_addr   shared address of the bf16 activation rows (hi block, lo block NB rows later), row stride xstride_b bytes
-//   kofs      first column of this chunk inside the activation rows
-template <int NB>
-NT_DEVINL void mma_consume_stage(uint32_t st, uint32_t xs_addr, uint32_t zero_addr, int xstride_b, int kc, int kofs, int ntiles,
-                                 float (&acc)[2][4]) {
-  constexpr bool kLo = NB <= 4;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int units = kc >> 5;  // k32 units in the chunk
-  const int u0 = (units * warp) / kConsumerWarps, u1 = (units * (warp + 1)) / kConsumerWarps;
-  const int lrow = lane & 7, lmat = lane >> 3;
-  const uint32_t wstride = static_cast<uint32_t>(kc) * 2u + 16u;
-  const uint32_t b_lane = st + lrow * wstride + lmat * 16;                       // + tile*8*wstride + k*2
-  const bool arow = lrow < NB;
-  const uint32_t a_lane = xs_addr + lrow * xstride_b + (lmat & 1) * 16 + kofs * 2;  // + k*2 (+ NB*xstride_b for lo)
-  for (int u = u0; u < u1; ++u) {
-    const uint32_t kb = static_cast<uint32_t>(u) * 64u;  // byte offset of this k32 unit
-    uint32_t ah[2][2], al[2][2];
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      ldsm_x2(arow ? a_lane + kb + s * 32 : zero_addr, ah[s][0], ah[s][1]);
-      if (kLo) ldsm_x2(arow ? a_lane + NB * xstride_b + kb + s * 32 : zero_addr, al[s][0], al[s][1]);
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (j < ntiles) {
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(b_lane + j * 8 * wstride + kb, b0, b1, b2, b3);
-        mma_bf16_16816(acc[j], ah[0][0], ah[0][1], b0, b1);
-        mma_bf16_16816(acc[j], ah[1][0], ah[1][1], b2, b3);
-        if (kLo) {
-          mma_bf16_16816(acc[j], al[0][0], al[0][1], b0, b1);
-          mma_bf16_16816(acc[j], al[1][0], al[1][1], b2, b3);
-        }
-      }
     }
   }
 }
@@ -673,54 +517,6 @@ NT_DEVINL void load_attn_merged(const AttnDecParams& p, const int* pos_cache, in
       for (int s = 0; s < 16; ++s) acc += wbuf[hh * 16 + s] * o[s];
       const int m4 = e >> 2;
       xf[(((2 * b + (m4 & 1)) * nch + (m4 >> 1)) << 2) + (e & 3)] = acc;
-    }
-  }
-  sync();
-}
-
-// Same merge, written as the bf16 hi(/lo) activation rows of the tensor-core path.
-template <int NB, typename Sync>
-NT_DEVINL void load_attn_merged_bf16(const AttnDecParams& p, const int* pos_cache, int split_cap, __nv_bfloat16* xs, float* wbuf, Sync sync) {
-  constexpr bool kLo = NB <= 4;
-  const int tid = threadIdx.x;
-  const int HD = p.n_heads * 64, xstride = HD + 8;
-  for (int i = tid; i < NB * p.n_heads; i += kConsumerThreads) {
-    const int b = i / p.n_heads;
-    const SplitGeom g = split_geom(pos_cache[b], p.kv.max_ctx, split_cap);
-    const float2* ml = reinterpret_cast<const float2*>(p.part_ml) + static_cast<long long>(i) * p.max_splits;
-    float2 v[16];
-#pragma unroll
-    for (int s = 0; s < 16; ++s) v[s] = (s < g.nsplit) ? __ldcg(ml + s) : make_float2(-INFINITY, 0.f);
-    float M = -INFINITY;
-#pragma unroll
-    for (int s = 0; s < 16; ++s) M = fmaxf(M, v[s].x);
-    float L = 0.f;
-#pragma unroll
-    for (int s = 0; s < 16; ++s) {
-      v[s].x = exp2f(v[s].x - M);
-      L += v[s].x * v[s].y;
-    }
-    const float inv = 1.0f / L;
-#pragma unroll
-    for (int s = 0; s < 16; ++s) wbuf[i * 16 + s] = v[s].x * inv;
-  }
-  sync();
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    const SplitGeom g = split_geom(pos_cache[b], p.kv.max_ctx, split_cap);
-    for (int e = tid; e < HD; e += kConsumerThreads) {
-      const int h = e >> 6, d = e & 63;
-      const long long hh = static_cast<long long>(b) * p.n_heads + h;
-      const float* po = p.part_o + hh * p.max_splits * 64 + d;
-      float o[16];
-#pragma unroll
-      for (int s = 0; s < 16; ++s) o[s] = (s < g.nsplit) ? __ldcg(po + s * 64) : 0.f;
-      float acc = 0.f;
-#pragma unroll
-      for (int s = 0; s < 16; ++s) acc += wbuf[hh * 16 + s] * o[s];
-      const __nv_bfloat16 hi = __float2bfloat16(acc);
-      xs[b * xstride + e] = hi;
-      if (kLo) xs[(NB + b) * xstride + e] = __float2bfloat16(acc - __bfloat162float(hi));
     }
   }
   sync();

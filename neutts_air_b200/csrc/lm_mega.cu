@@ -72,6 +72,21 @@ NT_DEVINL void grid_sync(unsigned* gbar, unsigned& target, unsigned nblocks, Pro
   asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
+struct PhaseSlice {
+  int u_begin, my_units, ups, stages, unit_bytes;
+};
+NT_DEVINL PhaseSlice phase_slice(const MegaPhase& ph) {
+  PhaseSlice s;
+  const int nunits = ph.rows >> 1;
+  s.u_begin = static_cast<int>((static_cast<long long>(nunits) * blockIdx.x) / gridDim.x);
+  const int u_end = static_cast<int>((static_cast<long long>(nunits) * (blockIdx.x + 1)) / gridDim.x);
+  s.my_units = u_end - s.u_begin;
+  s.ups = (ph.K >= 2048) ? 1 : kConsumerWarps;
+  s.stages = (s.my_units + s.ups - 1) / s.ups;
+  s.unit_bytes = 4 * ph.K;
+  return s;
+}
+
 NT_DEVINL void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -83,14 +98,13 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* ring = smem + P.ring_off;
-  __nv_bfloat16* xsb = reinterpret_cast<__nv_bfloat16*>(smem + P.x_off);  // bf16 hi(/lo) activation rows
+  float4* xs = reinterpret_cast<float4*>(smem + P.x_off);
   uint8_t* uni = smem + P.union_off;  // AttnSmem | head-phase logits + selector scratch ; x+uni together: final selection
-  uint8_t* zero16 = smem + P.misc_off;                                   // 16 zero bytes: padding rows of the MMA A operand
-  float2* red2 = reinterpret_cast<float2*>(zero16 + 128);                // [2 parity][2 tiles][8 warps][32 lanes]
-  float* s_part = reinterpret_cast<float*>(red2 + 2 * 2 * kConsumerWarps * 32);  // [8 warps][8 rows]
-  int* pos_cache = reinterpret_cast<int*>(s_part + 64);
-  int* page_cache = pos_cache + 8;
-  float* norm_buf = reinterpret_cast<float*>(page_cache + 8);
+  float* red = reinterpret_cast<float*>(smem + P.misc_off);
+  float* s_part = red + 2 * kConsumerWarps * 2 * 4;
+  int* pos_cache = reinterpret_cast<int*>(s_part + kConsumerWarps * 4);
+  int* page_cache = pos_cache + 4;
+  float* norm_buf = reinterpret_cast<float*>(page_cache + 4);
   float* bias_buf = norm_buf + P.hidden;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P.bar_off);
   uint64_t* empty_bar = full_bar + 8;
@@ -113,7 +127,6 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     fence_barrier_init();
     *s_go = 1;
   }
-  if (tid < 4) reinterpret_cast<uint32_t*>(zero16)[tid] = 0u;
   __syncthreads();
 
   if (warp == kConsumerWarps) {
@@ -134,43 +147,39 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
         for (int ph = 0; ph < n_phases; ++ph) {
           const int pidx = (ph == n_phases - 1) ? (4 * P.total_layers) : ph;  // lm_head is the last table entry
           if (P.l2_prefetch && (ph & 3) == 0 && ph < 4 * L) {
-            // entering layer l: pull this CTA's rows of layer l+1 (or the head of the lm_head slice) into L2
+            // entering layer l: pull this CTA's slices of layer l+1 (or the head of the lm_head slice) into L2
             const int l = ph >> 2;
             if (l + 1 < L) {
               for (int q = 0; q < 4; ++q) {
                 const MegaPhase np = P.phases[4 * (l + 1) + q];
-                const TileGeom ng = tile_geom(np.rows, np.K);
-                if (ng.r_end > ng.r_begin)
-                  bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(np.W) + static_cast<long long>(ng.r_begin) * np.K * 2,
-                                   static_cast<uint32_t>(ng.r_end - ng.r_begin) * np.K * 2);
+                const PhaseSlice ns = phase_slice(np);
+                if (ns.my_units > 0)
+                  bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(np.W) + static_cast<long long>(ns.u_begin) * ns.unit_bytes,
+                                   static_cast<uint32_t>(ns.my_units) * ns.unit_bytes);
               }
             }
             if (l + 2 >= L) {
               const MegaPhase hp = P.phases[4 * P.total_layers];
-              const TileGeom hg = tile_geom(hp.rows, hp.K);
-              const long long total = static_cast<long long>(hg.r_end - hg.r_begin) * hp.K * 2;
+              const PhaseSlice hs = phase_slice(hp);
+              const long long total = static_cast<long long>(hs.my_units) * hs.unit_bytes;
               const long long chunk = P.l2_head_bytes / 2;
               const long long off = (l + 2 == L) ? 0 : chunk;
               if (off < total)
-                bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(hp.W) + static_cast<long long>(hg.r_begin) * hp.K * 2 + off,
+                bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(hp.W) + static_cast<long long>(hs.u_begin) * hs.unit_bytes + off,
                                  static_cast<uint32_t>(min(chunk, total - off)) & ~15u);
             }
           }
           const MegaPhase mp = P.phases[pidx];
-          const TileGeom tg = tile_geom(mp.rows, mp.K);
-          const uint32_t row_bytes = static_cast<uint32_t>(tg.kc) * 2u;
-          for (int rb = 0; rb < tg.nrb; ++rb) {
-            const int row0 = tg.r_begin + rb * tg.rps;
-            const int nrows = min(tg.rps, tg.r_end - row0);
-            for (int kc = 0; kc < tg.nkc; ++kc, ++g) {
-              const int slot = g % NS;
-              if (g >= static_cast<uint32_t>(NS)) mbar_wait(&empty_bar[slot], ((g / NS) - 1) & 1);
-              mbar_arrive_expect_tx(&full_bar[slot], row_bytes * nrows);
-              uint8_t* dst = ring + static_cast<size_t>(slot) * P.stage_bytes;
-              const uint8_t* src = reinterpret_cast<const uint8_t*>(mp.W) + (static_cast<long long>(row0) * mp.K + kc * tg.kc) * 2;
-              for (int i = 0; i < nrows; ++i)  // one bulk copy per row: rows land 16 bytes apart from a 128-byte multiple
-                bulk_g2s(dst + i * (row_bytes + 16), src + static_cast<long long>(i) * mp.K * 2, row_bytes, &full_bar[slot]);
-            }
+          const PhaseSlice sl = phase_slice(mp);
+          const uint8_t* wbase = reinterpret_cast<const uint8_t*>(mp.W) + static_cast<long long>(sl.u_begin) * sl.unit_bytes;
+          for (int it = 0; it < sl.stages; ++it, ++g) {
+            const int slot = g % NS;
+            if (g >= static_cast<uint32_t>(NS)) mbar_wait(&empty_bar[slot], ((g / NS) - 1) & 1);
+            const int u0 = it * sl.ups;
+            const uint32_t bytes = static_cast<uint32_t>(min(sl.ups, sl.my_units - u0)) * sl.unit_bytes;
+            mbar_arrive_expect_tx(&full_bar[slot], bytes);
+            bulk_g2s(ring + static_cast<size_t>(slot) * P.stage_bytes, wbase + static_cast<long long>(u0) * sl.unit_bytes, bytes,
+                     &full_bar[slot]);
           }
         }
       }
@@ -187,16 +196,15 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
   const int H = P.hidden, I = P.inter, HD = P.n_heads * 64;
   const int n_rep = P.n_heads / P.kv.n_kv_heads;
   const int split_cap = P.split_cap;
-  const uint32_t xs_addr = smem_u32(xsb), zero_addr = smem_u32(zero16);
 
   // this CTA's slice of every layer's QKV bias (immutable) -> shared memory, once
-  const TileGeom qkv_g = tile_geom(P.qkv_n, H);
-  const int bias_rows = qkv_g.r_end - qkv_g.r_begin;
+  const PhaseSlice qkv_sl = phase_slice(P.phases[0]);
+  const int bias_rows = 2 * qkv_sl.my_units;
   const bool bias_cached = bias_rows <= P.bias_cap;
   if (bias_cached)
     for (int i = tid; i < L * bias_rows; i += kConsumerThreads) {
       const int l = i / bias_rows, r = i - l * bias_rows;
-      bias_buf[l * P.bias_cap + r] = __ldg(P.bqkv[l] + qkv_g.r_begin + r);
+      bias_buf[l * P.bias_cap + r] = __ldg(P.bqkv[l] + 2 * qkv_sl.u_begin + r);
     }
 
   auto prefetch_norm = [&](const float* w) {  // asynchronous global -> shared copy of one RMSNorm weight vector
@@ -204,45 +212,17 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     cp_async_commit();
   };
 
-  // one GEMV phase on the tensor cores: stages of (row block x K chunk), 8 warps split K, partial
-  // accumulators meet in shared memory once per row block, warps 0/1 run the fused epilogues
-  auto run_phase = [&](const GemvParams& gp, const TileGeom& tg, int K) {
+  auto run_stages = [&](const GemvParams& gp, const PhaseSlice& sl) {
     if (tid == 0) prof.mark();  // input vector staged
-    const int xstride_b = (K + 8) * 2;
-    int stage_no = 0;
-    for (int rb = 0; rb < tg.nrb; ++rb) {
-      float acc[2][4];
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[j][e] = 0.f;
-      const int row0 = tg.r_begin + rb * tg.rps;
-      const int nrows = min(tg.rps, tg.r_end - row0);
-      const int ntiles = (nrows + 7) >> 3;
-      for (int kc = 0; kc < tg.nkc; ++kc, ++g, ++stage_no) {
-        const int slot = g % NS;
-        mbar_wait(&full_bar[slot], (g / NS) & 1);
-        if (tid == 0 && (stage_no == 0 || stage_no == tg.stages - 1)) prof.mark();  // first / last stage landed
-        mma_consume_stage<NB>(smem_u32(ring + static_cast<size_t>(slot) * P.stage_bytes), xs_addr, zero_addr, xstride_b, tg.kc, kc * tg.kc,
-                              ntiles, acc);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[slot]);
-      }
-      float2* rbuf = red2 + (rb & 1) * (2 * kConsumerWarps * 32);
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        if (j < ntiles) rbuf[(j * kConsumerWarps + warp) * 32 + lane] = make_float2(acc[j][0], acc[j][1]);
-      csync();
-      if (warp < ntiles) {
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int w = 0; w < kConsumerWarps; ++w) {
-          const float2 v = rbuf[(warp * kConsumerWarps + w) * 32 + lane];
-          a0 += v.x, a1 += v.y;
-        }
-        const int b = lane >> 2, row = row0 + warp * 8 + 2 * (lane & 3);
-        if (b < NB && row < tg.r_end) unit_epilogue(gp, row >> 1, b, a0, a1);
-      }
+    for (int it = 0; it < sl.stages; ++it, ++g) {
+      const int slot = g % NS;
+      mbar_wait(&full_bar[slot], (g / NS) & 1);
+      if (tid == 0 && (it == 0 || it == sl.stages - 1)) prof.mark();  // first / last stage of the phase has landed
+      const int first = it * sl.ups;
+      gemv_consume_stage<NB>(gp, ring + static_cast<size_t>(slot) * P.stage_bytes, xs, red, sl.ups == 1 ? kConsumerWarps : 1, first,
+                             min(sl.ups, sl.my_units - first), sl.u_begin, it & 1, [&]() {
+                               if (lane == 0) mbar_arrive(&empty_bar[slot]);
+                             });
     }
   };
 
@@ -283,10 +263,10 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       gp.rows = P.qkv_n, gp.K = H, gp.eps = P.eps, gp.bias = P.bqkv[l];
       gp.epi = GEMV_QKV_ROPE, gp.q_out = P.q, gp.kv = P.kv, gp.layer = l, gp.n_heads = P.n_heads, gp.inv_freq = P.inv_freq;
       gp.pos_cache = pos_cache, gp.page_cache = page_cache;
-      if (bias_cached) gp.bias_smem = bias_buf + l * P.bias_cap, gp.row0 = qkv_g.r_begin;
+      if (bias_cached) gp.bias_smem = bias_buf + l * P.bias_cap, gp.row0 = 2 * qkv_sl.u_begin;
       cp_async_wait_all();
-      stage_x_bf16<NB>(P.h, H, H, norm_buf, P.eps, xsb, s_part, csync);
-      run_phase(gp, qkv_g, H);
+      load_x_planes<NB>(P.h, H, H, norm_buf, P.eps, xs, s_part, csync);
+      run_stages(gp, qkv_sl);
       ap.layer = l;
       if (can_prefetch_kv && tid == 0) attn_issue_page(ap, my_b, my_kvh, my_split * geo.pps, asmem, async_);
       grid_sync(P.gbar, target, G, prof);
@@ -297,38 +277,38 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       // ---- o_proj + residual (input = merged attention output)
       gp = GemvParams{};
       gp.rows = H, gp.K = HD, gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
-      load_attn_merged_bf16<NB>(ap, pos_cache, split_cap, xsb, reinterpret_cast<float*>(uni), csync);
-      run_phase(gp, tile_geom(H, HD), HD);
+      load_attn_merged<NB>(ap, pos_cache, split_cap, xs, reinterpret_cast<float*>(uni), csync);
+      run_stages(gp, phase_slice(P.phases[4 * l + 1]));
       grid_sync(P.gbar, target, G, prof);
       // ---- RMSNorm + gate/up + SiLU*up
       gp = GemvParams{};
       gp.rows = 2 * I, gp.K = H, gp.eps = P.eps, gp.epi = GEMV_SWIGLU, gp.out = P.act, gp.ldo = I;
       cp_async_wait_all();
-      stage_x_bf16<NB>(P.h, H, H, norm_buf, P.eps, xsb, s_part, csync);
+      load_x_planes<NB>(P.h, H, H, norm_buf, P.eps, xs, s_part, csync);
       prefetch_norm(l + 1 < L ? P.ln1[l + 1] : P.final_norm);  // norm_buf is free again: every thread passed the staging barrier
-      run_phase(gp, tile_geom(2 * I, H), H);
+      run_stages(gp, phase_slice(P.phases[4 * l + 2]));
       grid_sync(P.gbar, target, G, prof);
       // ---- down + residual
       gp = GemvParams{};
       gp.rows = H, gp.K = I, gp.epi = GEMV_STORE, gp.out = P.h, gp.ldo = H, gp.residual = P.h, gp.ldr = H;
-      stage_x_bf16<NB>(P.act, I, I, nullptr, 0.f, xsb, s_part, csync);
-      run_phase(gp, tile_geom(H, I), I);
+      load_x_planes<NB>(P.act, I, I, nullptr, 0.f, xs, s_part, csync);
+      run_stages(gp, phase_slice(P.phases[4 * l + 3]));
       grid_sync(P.gbar, target, G, prof);
     }
     // ---- lm_head (fused final RMSNorm); the CTA keeps its own logits in shared memory and selects its
     //      local top-64 per sequence right away (no second pass over the logits, no extra barrier)
     {
-      const TileGeom hg = tile_geom(P.vocab, H);
+      const PhaseSlice hs = phase_slice(P.phases[4 * P.total_layers]);
       float* lsm = reinterpret_cast<float*>(uni);
       GemvParams gp{};
       gp.rows = P.vocab, gp.K = H, gp.eps = P.eps, gp.epi = GEMV_STORE, gp.out = P.logits, gp.ldo = P.vocab;
-      gp.smem_out = lsm, gp.smem_ld = P.head_ld, gp.row0 = hg.r_begin;
+      gp.smem_out = lsm, gp.smem_ld = P.head_ld, gp.row0 = 2 * hs.u_begin;
       cp_async_wait_all();
-      stage_x_bf16<NB>(P.h, H, H, norm_buf, P.eps, xsb, s_part, csync);
-      run_phase(gp, hg, H);
+      load_x_planes<NB>(P.h, H, H, norm_buf, P.eps, xs, s_part, csync);
+      run_stages(gp, hs);
       csync();
       uint32_t* scratch = reinterpret_cast<uint32_t*>(lsm + NB * P.head_ld);
-      const int n_local = hg.r_end - hg.r_begin;
+      const int n_local = 2 * hs.my_units;
       const float inv_t = 1.0f / P.samp.sp.temperature;
 #pragma unroll 1
       for (int b = 0; b < NB; ++b) {
@@ -350,7 +330,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     // ---- final selection: CTA b finishes sequence b (top-k over G*64 candidates, softmax, draw, state, next embedding)
     if (static_cast<int>(blockIdx.x) < NB) {
       const int ncand = static_cast<int>(G) * kTopKeep;
-      uint32_t* keys = reinterpret_cast<uint32_t*>(xsb);  // x rows + union region are contiguous and idle here
+      uint32_t* keys = reinterpret_cast<uint32_t*>(xs);  // x planes + union region are contiguous and idle here
       uint32_t* scratch = keys + ncand;
       Cand* win = reinterpret_cast<Cand*>(scratch + kSelScratch);
       int* s_tok = reinterpret_cast<int*>(win + 2 * kTopKeep);
@@ -370,35 +350,19 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
   if (tid == 0) *s_go = -1;
 }
 
-bool mega_supported(int hidden, int inter, int n_heads, int batch) {
-  auto ok = [](int K) {
-    const int nkc = (K <= 1024) ? 1 : (K + 1535) / 1536;
-    return K % (32 * nkc) == 0;
-  };
-  return batch >= 1 && batch <= 8 && ok(hidden) && ok(inter) && ok(n_heads * 64);
-}
-
 int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream) {
-  if (!mega_supported(P.hidden, P.inter, P.n_heads, nb)) return set_error(NT_ERR_INVALID, "megakernel: unsupported shape / batch %d", nb);
+  if (nb < 1 || nb > 4) return set_error(NT_ERR_INVALID, "megakernel: batch %d not in 1..4", nb);
   if (num_sms > 256) num_sms = 256;
   // ---- shared-memory plan
   const int HD = P.n_heads * 64;
-  auto stage_of = [](int K) {
-    const int nkc = (K <= 1024) ? 1 : (K + 1535) / 1536;
-    return (nkc == 1 ? 16 : 8) * ((K / nkc) * 2 + 16);
-  };
-  int stage = stage_of(P.hidden);
-  if (stage_of(P.inter) > stage) stage = stage_of(P.inter);
-  if (stage_of(HD) > stage) stage = stage_of(HD);
+  const int k_small = P.hidden, k_big = P.inter > HD ? P.inter : HD;
+  auto unit_stage = [](int K) { return (K >= 2048 ? 1 : kConsumerWarps) * 4 * K; };
+  int stage = unit_stage(P.hidden);
+  if (unit_stage(P.inter) > stage) stage = unit_stage(P.inter);
+  if (unit_stage(HD) > stage) stage = unit_stage(HD);
   stage = (stage + 127) & ~127;
-  const int parts = nb <= 4 ? 2 : 1;
-  int kmax = P.hidden > P.inter ? P.hidden : P.inter;
-  if (HD > kmax) kmax = HD;
-  size_t x_bytes = size_t(parts) * nb * (kmax + 8) * 2;
-  const size_t x_norm = size_t(parts) * nb * (P.hidden + 8) * 2 + size_t(nb) * P.hidden * 4;  // bf16 rows + fp32 scratch of a norm phase
-  if (x_norm > x_bytes) x_bytes = x_norm;
-  x_bytes = (x_bytes + 127) & ~size_t(127);
-  // union region: attention staging | head-phase logits (nb rows) + selector scratch | merge weights
+  const size_t x_bytes = (size_t(nb) * (k_big > k_small ? k_big : k_small) * 4 + 127) & ~size_t(127);
+  // union region: attention staging | head-phase logits (nb rows) + selector scratch
   P.head_ld = 2 * ((P.vocab / 2 + num_sms - 1) / num_sms) + 8;
   size_t uni = size_t(nb) * P.head_ld * 4 + kSelScratch * 4 + 64;
   if (sizeof(AttnSmem) > uni) uni = sizeof(AttnSmem);
@@ -406,9 +370,10 @@ int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream) 
   // the final selection needs G*64 keys + scratch + winners inside x + union
   const size_t final_need = size_t(num_sms) * kTopKeep * 4 + kSelScratch * 4 + 2 * kTopKeep * sizeof(Cand) + 64;
   if (x_bytes + uni < final_need) uni = ((final_need - x_bytes) + 127) & ~size_t(127);
-  P.bias_cap = 2 * ((P.qkv_n / 2 + num_sms - 1) / num_sms) + 2;
+  const int qkv_units = P.qkv_n / 2;
+  P.bias_cap = 2 * ((qkv_units + num_sms - 1) / num_sms) + 2;
   if (P.bias_cap > 64) P.bias_cap = 0;  // huge slices: read the bias from global memory instead
-  const size_t misc = (128 + 2 * 2 * kConsumerWarps * 32 * sizeof(float2) + 64 * sizeof(float) + 16 * sizeof(int) + size_t(P.hidden) * 4 +
+  const size_t misc = ((2 * kConsumerWarps * 2 * 4 + kConsumerWarps * 4) * sizeof(float) + 8 * sizeof(int) + size_t(P.hidden) * 4 +
                        size_t(P.total_layers) * P.bias_cap * 4 + 127) & ~size_t(127);
   const size_t bars = (16 * sizeof(uint64_t) + sizeof(AttnSync) + 16 + 127) & ~size_t(127);
   const size_t fixed = x_bytes + uni + misc + bars + 128;
@@ -437,13 +402,9 @@ int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream) 
     case 1: kern = decode_mega_kernel<1>; break;
     case 2: kern = decode_mega_kernel<2>; break;
     case 3: kern = decode_mega_kernel<3>; break;
-    case 4: kern = decode_mega_kernel<4>; break;
-    case 5: kern = decode_mega_kernel<5>; break;
-    case 6: kern = decode_mega_kernel<6>; break;
-    case 7: kern = decode_mega_kernel<7>; break;
-    default: kern = decode_mega_kernel<8>; break;
+    default: kern = decode_mega_kernel<4>; break;
   }
-  static size_t attr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  static size_t attr[5] = {0, 0, 0, 0, 0};
   if (attr[nb] < smem) {
     NT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     attr[nb] = smem;

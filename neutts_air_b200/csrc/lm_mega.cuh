@@ -45,6 +45,5 @@ struct MegaParams {
 
 constexpr int kProfMarks = 1024;
 int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream);
-bool mega_supported(int hidden, int inter, int n_heads, int batch);
 
 }  // namespace nt
