@@ -64,6 +64,8 @@ struct nt_lm {
   // cached decode-step graph
   cudaGraphExec_t graph = nullptr;
   std::vector<uint8_t> graph_key;
+  cudaStream_t grp_stream[4] = {nullptr, nullptr, nullptr, nullptr};  // concurrent megakernel instances (batch 5..16)
+  cudaEvent_t grp_fork = nullptr, grp_join[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaStream_t cap_stream = nullptr;  // capture happens here (torch's default stream is the legacy
                                       // stream, which cannot be captured); replay on the caller's stream
   uint64_t graph_kernels = 0;         // kernel nodes in the captured step (for nt_launch_count)
@@ -208,9 +210,14 @@ extern "C" int nt_lm_create(const nt_lm_config* cfg, const nt_lm_weights* w, voi
       return set_error(NT_ERR_CUDA, "megakernel table upload failed");
     }
   }
-  if (cudaStreamCreateWithFlags(&lm->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  bool ok = cudaStreamCreateWithFlags(&lm->cap_stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&lm->grp_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < 4 && ok; ++i)
+    ok = cudaStreamCreateWithFlags(&lm->grp_stream[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&lm->grp_join[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
     delete lm;
-    return set_error(NT_ERR_CUDA, "stream creation failed");
+    return set_error(NT_ERR_CUDA, "stream / event creation failed");
   }
   *out = lm;
   return NT_OK;
@@ -220,6 +227,11 @@ extern "C" int nt_lm_destroy(nt_lm* lm) {
   if (!lm) return NT_OK;
   if (lm->graph) cudaGraphExecDestroy(lm->graph);
   if (lm->cap_stream) cudaStreamDestroy(lm->cap_stream);
+  if (lm->grp_fork) cudaEventDestroy(lm->grp_fork);
+  for (int i = 0; i < 4; ++i) {
+    if (lm->grp_stream[i]) cudaStreamDestroy(lm->grp_stream[i]);
+    if (lm->grp_join[i]) cudaEventDestroy(lm->grp_join[i]);
+  }
   delete lm;
   return NT_OK;
 }
@@ -438,28 +450,59 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
   if (n_steps < 0) return set_error(NT_ERR_INVALID, "negative step count");
 
   if (n_steps == 0) return NT_OK;
-  if (B <= 4 && !env_flag("NT_NO_MEGA") && c.hidden % 64 == 0) {
-    // persistent megakernel: every layer, the lm_head, the sampler and all n_steps in one launch
-    MegaParams P;
-    memset(&P, 0, sizeof(P));
-    P.n_layers = lm->debug_layers >= 0 ? lm->debug_layers : c.n_layers;
-    P.total_layers = c.n_layers;
-    P.hidden = c.hidden, P.inter = c.inter, P.n_heads = c.n_heads, P.qkv_n = lm->qkv_n, P.vocab = c.vocab_size;
-    P.eps = c.rms_eps, P.scale_log2 = (1.0f / 8.0f) * 1.4426950408889634f;
-    P.phases = lm->phase_tab;
-    P.ln1 = lm->ptr_tab, P.bqkv = lm->ptr_tab + c.n_layers, P.ln2 = lm->ptr_tab + 2 * c.n_layers;
-    P.final_norm = lm->final_norm, P.inv_freq = lm->inv_freq;
-    P.h = lm->h, P.q = lm->q, P.attn = lm->attn, P.act = lm->act, P.logits = lm->logits;
-    P.kv = make_kv(lm, st);
-    P.part_o = lm->part_o, P.part_ml = lm->part_ml, P.counters = lm->counters, P.max_splits = lm->max_splits;
-    P.samp = make_sampler(lm, st, sp);
-    P.samp.advance = 1;
-    P.gbar = lm->gbar;
-    P.n_steps = n_steps;
-    P.logits_out = logits_out;
-    P.prof = lm->prof, P.prof_step = lm->prof_step;
-    if ((rc = launch_sampler_check(P.samp))) return rc;
-    return launch_decode_mega(P, B, lm->num_sms, stream);
+  if (B <= 16 && !env_flag("NT_NO_MEGA") && c.hidden % 64 == 0) {
+    // Persistent megakernel: every layer, the lm_head, the sampler and all n_steps in one launch.
+    // Batch 5..16 runs as up to four concurrent instances of <= 4 sequences on disjoint SM subsets
+    // (each streams the full weights; the decode step is latency-bound, HBM has the headroom).
+    const int ngroups = (B + 3) / 4;
+    const int per = (B + ngroups - 1) / ngroups;
+    const int sms = lm->num_sms / ngroups;
+    const int splits_stride = lm->max_splits;
+    if (ngroups > 1) NT_CUDA_CHECK(cudaEventRecord(lm->grp_fork, stream));
+    for (int gi = 0; gi < ngroups; ++gi) {
+      const int b0 = gi * per, nb = (B - b0 < per) ? (B - b0) : per;
+      cudaStream_t gs = ngroups > 1 ? lm->grp_stream[gi] : stream;
+      if (ngroups > 1) NT_CUDA_CHECK(cudaStreamWaitEvent(gs, lm->grp_fork, 0));
+      MegaParams P;
+      memset(&P, 0, sizeof(P));
+      P.n_layers = lm->debug_layers >= 0 ? lm->debug_layers : c.n_layers;
+      P.total_layers = c.n_layers;
+      P.hidden = c.hidden, P.inter = c.inter, P.n_heads = c.n_heads, P.qkv_n = lm->qkv_n, P.vocab = c.vocab_size;
+      P.eps = c.rms_eps, P.scale_log2 = (1.0f / 8.0f) * 1.4426950408889634f;
+      P.phases = lm->phase_tab;
+      P.ln1 = lm->ptr_tab, P.bqkv = lm->ptr_tab + c.n_layers, P.ln2 = lm->ptr_tab + 2 * c.n_layers;
+      P.final_norm = lm->final_norm, P.inv_freq = lm->inv_freq;
+      const int HD = c.n_heads * 64;
+      P.h = lm->h + size_t(b0) * c.hidden, P.q = lm->q + size_t(b0) * HD, P.attn = lm->attn + size_t(b0) * HD;
+      P.act = lm->act + size_t(b0) * c.inter, P.logits = lm->logits + size_t(b0) * c.vocab_size;
+      P.kv = make_kv(lm, st);
+      P.kv.page_table += size_t(b0) * P.kv.max_pages_per_seq;
+      P.kv.seq_lens += b0;
+      P.part_o = lm->part_o + size_t(b0) * c.n_heads * splits_stride * 64;
+      P.part_ml = lm->part_ml + size_t(b0) * c.n_heads * splits_stride * 2;
+      P.counters = lm->counters, P.max_splits = lm->max_splits;
+      P.samp = make_sampler(lm, st, sp);
+      P.samp.advance = 1;
+      P.samp.slot_base = b0;
+      P.samp.logits = P.logits;
+      P.samp.seq_lens += b0, P.samp.cur_token += b0, P.samp.n_generated += b0, P.samp.done += b0;
+      P.samp.out_tokens += size_t(b0) * st->max_new;
+      if (P.samp.sp.forced) P.samp.sp.forced += size_t(b0) * st->max_new;
+      P.samp.cand_val += size_t(b0) * 256 * 64, P.samp.cand_idx += size_t(b0) * 256 * 64;
+      P.samp.h = P.h;
+      P.gbar = lm->gbar + 64 * gi;
+      P.n_steps = n_steps;
+      P.logits_out = logits_out ? logits_out + size_t(b0) * c.vocab_size : nullptr;
+      P.logits_step_stride = static_cast<long long>(B) * c.vocab_size;
+      P.prof = gi == 0 ? lm->prof : nullptr, P.prof_step = lm->prof_step;
+      if ((rc = launch_sampler_check(P.samp))) return rc;
+      if ((rc = launch_decode_mega(P, nb, sms, gs))) return rc;
+      if (ngroups > 1) {
+        NT_CUDA_CHECK(cudaEventRecord(lm->grp_join[gi], gs));
+        NT_CUDA_CHECK(cudaStreamWaitEvent(stream, lm->grp_join[gi], 0));
+      }
+    }
+    return NT_OK;
   }
 
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;

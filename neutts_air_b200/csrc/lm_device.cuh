@@ -819,7 +819,7 @@ NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint3
       } else if (p.sp.greedy) {
         tok = win[0].i;
       } else {
-        uint32_t ctr[4] = {static_cast<uint32_t>(stateless ? p.step_override : ngen), static_cast<uint32_t>(b), 0u, 0u};
+        uint32_t ctr[4] = {static_cast<uint32_t>(stateless ? p.step_override : ngen), static_cast<uint32_t>(b + p.slot_base), 0u, 0u};
         philox4x32_10(ctr, static_cast<uint32_t>(p.sp.seed), static_cast<uint32_t>(p.sp.seed >> 32));
         const float u = (ctr[0] >> 8) * (1.0f / 16777216.0f);  // [0,1)
         const float target = u * sum;

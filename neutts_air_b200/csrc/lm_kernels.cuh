@@ -89,6 +89,7 @@ struct SamplerParams {
   int32_t* dbg_token;      // [B]
   const int32_t* n_generated_override;  // nt_op_topk_sample: read-only counters, no state update
   int32_t step_override;
+  int32_t slot_base;  // global slot index of local sequence 0 (keys the Philox counter; grouped megakernel launches)
 };
 int launch_sampler(const SamplerParams& p, int B, cudaStream_t stream);
 int launch_sampler_check(const SamplerParams& p);

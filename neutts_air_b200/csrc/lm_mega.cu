@@ -323,7 +323,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     grid_sync(P.gbar, target, G, prof);
     if (P.logits_out) {  // tests: keep every step's logits
       const long long n = static_cast<long long>(NB) * P.vocab;
-      float* dst = P.logits_out + static_cast<long long>(step) * n;
+      float* dst = P.logits_out + static_cast<long long>(step) * P.logits_step_stride;
       for (long long i = static_cast<long long>(blockIdx.x) * kConsumerThreads + tid; i < n; i += static_cast<long long>(G) * kConsumerThreads)
         dst[i] = __ldcg(P.logits + i);
     }
@@ -412,7 +412,7 @@ int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream) 
   int per_sm = 0;
   NT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (kConsumerWarps + 1) * 32, smem));
   if (per_sm < 1) return set_error(NT_ERR_CUDA, "megakernel: a CTA does not fit on an SM (%zu B shared memory)", smem);
-  NT_CUDA_CHECK(cudaMemsetAsync(P.gbar, 0, sizeof(unsigned) * 256, stream));
+  NT_CUDA_CHECK(cudaMemsetAsync(P.gbar, 0, sizeof(unsigned) * 64, stream));  // one counter per instance, 256 B apart
   void* args[] = {&P};
   cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(num_sms), dim3((kConsumerWarps + 1) * 32), args, smem, stream);
   if (e != cudaSuccess) return set_error(NT_ERR_CUDA, "megakernel launch failed: %s", cudaGetErrorString(e));

@@ -30,7 +30,8 @@ struct MegaParams {
   SamplerParams samp;
   unsigned* gbar;     // grid barrier counter, zeroed before every launch
   int n_steps;
-  float* logits_out;  // optional [n_steps][nb][vocab]
+  float* logits_out;  // optional: this group's first row of [n_steps][batch][vocab]
+  long long logits_step_stride;  // elements between consecutive steps in logits_out (batch * vocab)
   long long* prof;    // optional timeline buffer [2 CTAs][kProfMarks] of %globaltimer ns (profiles/probe_mega.py)
   int prof_step;
   // shared-memory plan and tuning (filled by launch_decode_mega)

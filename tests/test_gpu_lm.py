@@ -103,20 +103,23 @@ def test_lm_ragged_batch_prefill_and_decode(cuda, mega, monkeypatch):
         assert rel_err(got[b], mir) < 6e-3 and max_err(got[b], mir) < 5e-2 * float(mir.std()), (b, rel_err(got[b], mir))
 
 
-@pytest.mark.parametrize("B", [6, 10], ids=["megakernel-bf16-acts", "per-op-tcgen05"])
+@pytest.mark.parametrize("B", [6, 10, 18], ids=["2-megakernel-instances", "3-megakernel-instances", "per-op-tcgen05"])
 def test_lm_batched_decode(cuda, B):
-    """batch 5..8 runs in the megakernel with single-bf16 activations; batch > 8 decodes through the
-    per-op tcgen05 GEMM path with M = batch.  Both round GEMM inputs to bf16, so they are held to the
-    pure-reference bar."""
-    cfg, w, lm = _setup(SMALL, 31, max_batch=16, max_ctx=256)
+    """batch 5..16 runs as concurrent megakernel instances of <= 4 sequences on disjoint SM subsets (fp32
+    activations, same arithmetic as batch 1); batch > 16 decodes through the per-op tcgen05 GEMM path with
+    M = batch (bf16 GEMM inputs).  Prefill is the tensor-core path in every case, so the bar is the
+    pure-reference one."""
+    cfg, w, lm = _setup(SMALL, 31, max_batch=20, max_ctx=256)
     g = torch.Generator().manual_seed(2)
-    lens, n_new, eos = [20, 41, 64, 65, 9, 30, 17, 80, 33, 5][:B], 4, cfg.vocab_size - 1
+    lens = [20, 41, 64, 65, 9, 30, 17, 80, 33, 5, 12, 70, 3, 44, 27, 90, 61, 8][:B]
+    n_new, eos = 4, cfg.vocab_size - 1
     prompts = [torch.randint(0, cfg.vocab_size, (n,), generator=g) for n in lens]
     forced = torch.randint(0, cfg.vocab_size, (B, n_new), generator=g)
     got = _teacher_forced(cfg, w, lm, [p.tolist() for p in prompts], forced, n_new, eos)
     for b, p in enumerate(prompts):
         _, ref = O.generate(cfg, w, p, eos, max_length=256, max_new_tokens=n_new, forced=forced[b], mirror=False)
         assert rel_err(got[b], ref) < 2e-2 and max_err(got[b], ref) < 1e-1 * float(ref.std()), (b, rel_err(got[b], ref))
+    assert lm.out_tokens[:B, :n_new].cpu().tolist() == forced.tolist()
 
 
 def test_lm_generate_stops_and_graph_replay(cuda):
