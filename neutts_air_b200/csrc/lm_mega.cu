@@ -212,9 +212,10 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     cp_async_commit();
   };
 
-  auto run_stages = [&](const GemvParams& gp, const PhaseSlice& sl) {
-    if (tid == 0) prof.mark();  // input vector staged
-    for (int it = 0; it < sl.stages; ++it, ++g) {
+  auto run_stages = [&](const GemvParams& gp, const PhaseSlice& sl, int it0 = 0, int it1 = -1) {
+    if (it1 < 0) it1 = sl.stages;
+    if (tid == 0 && it0 == 0) prof.mark();  // input vector staged
+    for (int it = it0; it < it1; ++it, ++g) {
       const int slot = g % NS;
       mbar_wait(&full_bar[slot], (g / NS) & 1);
       if (tid == 0 && (it == 0 || it == sl.stages - 1)) prof.mark();  // first / last stage of the phase has landed
@@ -295,29 +296,38 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
       run_stages(gp, phase_slice(P.phases[4 * l + 3]));
       grid_sync(P.gbar, target, G, prof);
     }
-    // ---- lm_head (fused final RMSNorm); the CTA keeps its own logits in shared memory and selects its
-    //      local top-64 per sequence right away (no second pass over the logits, no extra barrier)
+    // ---- lm_head (fused final RMSNorm); the CTA keeps its own logits in shared memory and selects a local
+    //      top-64 per sequence right away (no second pass over the logits, no extra barrier).  With a small
+    //      grid (concurrent instances) the CTA's rows are processed in segments of head_ld rows.
     {
       const PhaseSlice hs = phase_slice(P.phases[4 * P.total_layers]);
       float* lsm = reinterpret_cast<float*>(uni);
       GemvParams gp{};
       gp.rows = P.vocab, gp.K = H, gp.eps = P.eps, gp.epi = GEMV_STORE, gp.out = P.logits, gp.ldo = P.vocab;
-      gp.smem_out = lsm, gp.smem_ld = P.head_ld, gp.row0 = 2 * hs.u_begin;
+      gp.smem_out = lsm, gp.smem_ld = P.head_ld;
       cp_async_wait_all();
       load_x_planes<NB>(P.h, H, H, norm_buf, P.eps, xs, s_part, csync);
-      run_stages(gp, hs);
-      csync();
       uint32_t* scratch = reinterpret_cast<uint32_t*>(lsm + NB * P.head_ld);
-      const int n_local = 2 * hs.my_units;
       const float inv_t = 1.0f / P.samp.sp.temperature;
-#pragma unroll 1
-      for (int b = 0; b < NB; ++b) {
-        const bool mask_eos = __ldcg(P.samp.n_generated + b) < P.samp.sp.min_new_tokens;
-        uint32_t* keys = reinterpret_cast<uint32_t*>(lsm + b * P.head_ld);
-        for (int e = tid; e < n_local; e += kConsumerThreads)
-          keys[e] = processed_key(lsm[b * P.head_ld + e], gp.row0 + e, mask_eos, P.samp.sp.eos_id, inv_t);
+      const int seg_stages = P.head_ld / (2 * hs.ups);  // stages per segment (ups units = 2*ups rows per stage)
+      for (int seg = 0; seg < P.head_segs; ++seg) {
+        const int it0 = seg * seg_stages, it1 = min(hs.stages, it0 + seg_stages);
+        const int first_row = 2 * (hs.u_begin + it0 * hs.ups);
+        const int n_local = max(0, min(2 * hs.my_units - 2 * it0 * hs.ups, 2 * (it1 - it0) * hs.ups));
+        gp.row0 = first_row;
+        if (it0 < it1) run_stages(gp, hs, it0, it1);
         csync();
-        emit_local_topk(P.samp, keys, n_local, gp.row0, (static_cast<long long>(b) * G + blockIdx.x) * kTopKeep, scratch, csync);
+#pragma unroll 1
+        for (int b = 0; b < NB; ++b) {
+          const bool mask_eos = __ldcg(P.samp.n_generated + b) < P.samp.sp.min_new_tokens;
+          uint32_t* keys = reinterpret_cast<uint32_t*>(lsm + b * P.head_ld);
+          for (int e = tid; e < n_local; e += kConsumerThreads)
+            keys[e] = processed_key(lsm[b * P.head_ld + e], first_row + e, mask_eos, P.samp.sp.eos_id, inv_t);
+          csync();
+          emit_local_topk(P.samp, keys, n_local, first_row,
+                          ((static_cast<long long>(b) * G + blockIdx.x) * P.head_segs + seg) * kTopKeep, scratch, csync);
+        }
+        csync();
       }
     }
     grid_sync(P.gbar, target, G, prof);
@@ -329,7 +339,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     }
     // ---- final selection: CTA b finishes sequence b (top-k over G*64 candidates, softmax, draw, state, next embedding)
     if (static_cast<int>(blockIdx.x) < NB) {
-      const int ncand = static_cast<int>(G) * kTopKeep;
+      const int ncand = static_cast<int>(G) * P.head_segs * kTopKeep;
       uint32_t* keys = reinterpret_cast<uint32_t*>(xs);  // x planes + union region are contiguous and idle here
       uint32_t* scratch = keys + ncand;
       Cand* win = reinterpret_cast<Cand*>(scratch + kSelScratch);
@@ -363,12 +373,15 @@ int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream) 
   stage = (stage + 127) & ~127;
   const size_t x_bytes = (size_t(nb) * (k_big > k_small ? k_big : k_small) * 4 + 127) & ~size_t(127);
   // union region: attention staging | head-phase logits (nb rows) + selector scratch
-  P.head_ld = 2 * ((P.vocab / 2 + num_sms - 1) / num_sms) + 8;
+  const int head_rows = 2 * ((P.vocab / 2 + num_sms - 1) / num_sms);  // rows of the lm_head per CTA (max)
+  P.head_ld = head_rows < 1536 ? ((head_rows + 15) & ~15) : 1536;         // rows kept in shared memory per segment
+  P.head_segs = (head_rows + P.head_ld - 1) / P.head_ld;
+  if (num_sms * P.head_segs > 256) return set_error(NT_ERR_INVALID, "megakernel: vocabulary too large for the candidate arrays");
   size_t uni = size_t(nb) * P.head_ld * 4 + kSelScratch * 4 + 64;
   if (sizeof(AttnSmem) > uni) uni = sizeof(AttnSmem);
   uni = (uni + 127) & ~size_t(127);
   // the final selection needs G*64 keys + scratch + winners inside x + union
-  const size_t final_need = size_t(num_sms) * kTopKeep * 4 + kSelScratch * 4 + 2 * kTopKeep * sizeof(Cand) + 64;
+  const size_t final_need = size_t(num_sms) * P.head_segs * kTopKeep * 4 + kSelScratch * 4 + 2 * kTopKeep * sizeof(Cand) + 64;
   if (x_bytes + uni < final_need) uni = ((final_need - x_bytes) + 127) & ~size_t(127);
   const int qkv_units = P.qkv_n / 2;
   P.bias_cap = 2 * ((qkv_units + num_sms - 1) / num_sms) + 2;

@@ -36,7 +36,8 @@ struct MegaParams {
   int prof_step;
   // shared-memory plan and tuning (filled by launch_decode_mega)
   int nstages, stage_bytes;
-  int head_ld;        // row length of the per-CTA logits copy kept in shared memory during the lm_head phase
+  int head_ld;        // rows of the per-CTA logits copy kept in shared memory per lm_head segment
+  int head_segs;      // segments the CTA's lm_head rows are processed in (1 on a full-chip grid)
   int bias_cap;       // per-layer slots of the cached QKV bias slice (0 = not cached)
   int split_cap;      // attention splits per (sequence, kv head): 16 / batch
   int l2_prefetch;    // producer prefetches the next layer's slices into L2
