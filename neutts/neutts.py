@@ -280,17 +280,13 @@ class NeuTTS:
         cache = list(ref_codes)              # code history: reference codes, then generated ones
         n_dec = len(cache)
         fade = _CrossFade(self.streaming_stride_samples)
-        lm.prefill([prompt], sp)
-        produced, finished = 0, False
-        while not finished:
-            need = F + LA - (len(cache) - n_dec)
-            if produced + 1 < limit and need > 0:
-                lm.decode(min(need, limit - 1 - produced), sp)
+        lm.prefill([prompt], sp)             # samples the first token
+        produced = 0
+        while True:
             ngen = int(lm.n_generated[0])
             finished = bool(int(lm.done[0])) or ngen >= limit
-            new = lm.out_tokens[0, produced:ngen].cpu()
+            cache += self._ids_to_codes(lm.out_tokens[0, produced:ngen].cpu()).tolist()
             produced = ngen
-            cache += self._ids_to_codes(new).tolist()
             while len(cache) - n_dec >= F + LA:
                 t0 = max(n_dec - LB - OV, 0)
                 # the reference slices up to n_dec + F + LA + OV, but tokens arrive one at a time there, so
@@ -300,6 +296,10 @@ class NeuTTS:
                 wav = self._watermark(self._decode(cache[t0:t1]))[s0: s0 + (F + 2 * OV) * hop]
                 n_dec += F
                 yield fade.push(wav)
+            if finished:
+                break
+            # decode just enough steps for the next chunk to fire (non-speech ids may make it take another pass)
+            lm.decode(min(F + LA - (len(cache) - n_dec), limit - ngen), sp)
         if len(cache) > n_dec:               # ragged tail (neutts/neutts.py:443-465)
             rem = len(cache) - n_dec
             t0 = max(len(cache) - (LB + OV + rem), 0)

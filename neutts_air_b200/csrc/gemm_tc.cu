@@ -26,6 +26,8 @@ struct GemmEpilogue {
   __nv_bfloat16* out_bf16;
   long long ldc;
   int valid_period, valid_len;
+  int split_k;             // > 1: grid.z K-slices; slice z stores its raw partial sums at out_f32 + z * split_stride
+  long long split_stride;  // (no residual / activation; bias rides on slice 0) -- the consumer adds them in z order
 };
 
 template <int BN>
@@ -60,6 +62,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int lane = lane_id();
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * Cfg::BM;
+  // split-K: this CTA owns k-blocks [kb_lo, kb_hi)
+  const int kb_lo = ep.split_k > 1 ? static_cast<int>((static_cast<long long>(num_kb) * blockIdx.z) / ep.split_k) : 0;
+  const int kb_hi = ep.split_k > 1 ? static_cast<int>((static_cast<long long>(num_kb) * (blockIdx.z + 1)) / ep.split_k) : num_kb;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -84,9 +89,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        const int s = (kb - kb_lo) % STAGES;
+        const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         uint8_t* sa = tiles + s * Cfg::STAGE_BYTES;
@@ -101,9 +106,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(kFmt, 128, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
+      for (int kb = kb_lo; kb < kb_hi; ++kb) {
+        const int s = (kb - kb_lo) % STAGES;
+        const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(tiles + s * Cfg::STAGE_BYTES);
@@ -112,7 +117,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint64_t bdesc = umma_desc_sw128(sb);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per stage
-          const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+          const uint32_t acc = (kb > kb_lo || k > 0) ? 1u : 0u;
           if (kFmt == 2)
             umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
           else
@@ -142,6 +147,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
       const bool full = (col0 + 32 <= N);
+      if (ep.split_k > 1) {
+        float* dst = ep.out_f32 + blockIdx.z * ep.split_stride + row * ep.ldc + col0;
+        if (ep.bias && blockIdx.z == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || col0 + j < N) v[j] += __ldg(ep.bias + col0 + j);
+        }
+        if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) dst[j] = v[j];
+        }
+        continue;
+      }
       if (ep.bias) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -261,6 +282,7 @@ static int make_tmap(CUtensorMap* out, nt_dtype dt, const void* base, uint64_t r
 template <int kFmt, int BN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int num_kb,
                        int kb_per_tap, cudaStream_t stream) {
+  const int splits = ep.split_k > 1 ? ep.split_k : 1;
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   auto kern = gemm_tc_kernel<kFmt, BN>;
@@ -268,12 +290,12 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
     NT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + Cfg::BM - 1) / Cfg::BM, 1);
+  dim3 grid((N + BN - 1) / BN, (M + Cfg::BM - 1) / Cfg::BM, splits);
   return launch_kernel(kern, grid, dim3(256), Cfg::SMEM_BYTES, stream, /*pdl=*/true, ta, tb, ep, M, N, num_kb,
                        kb_per_tap);
 }
 
-int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream) {
+int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error(NT_ERR_INVALID, "gemm: empty problem");
   const int esz = a.dtype == NT_BF16 ? 2 : 4;
   const int bk = 128 / esz;
@@ -321,6 +343,26 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream) {
   ep.ldc = a.ldc;
   ep.valid_period = a.valid_period;
   ep.valid_len = a.valid_len;
+  // split-K (only when the caller lends a workspace and will fold the slices itself): few tiles would leave most
+  // SMs idle, so grid.z slices of the K loop store raw partial sums; the summation order stays fixed (z order)
+  ep.split_k = 1;
+  ep.split_stride = 0;
+  if (split) {
+    split->used = 1;
+    const int tiles = mt * ((a.N + bn - 1) / bn);
+    if (tiles <= 48 && taps == 1 && a.act == NT_ACT_NONE && !a.out_bf16 && a.out_f32 && a.residual == a.out_f32 && a.ldr == a.ldc &&
+        a.valid_period == 0 && num_kb >= 8) {
+      int sk = 144 / tiles;
+      if (sk > num_kb / 4) sk = num_kb / 4;
+      if (sk > 8) sk = 8;
+      const size_t slice = size_t(a.M) * size_t(a.ldc);
+      if (sk > 1 && slice * sk <= split->ws_floats) {
+        ep.split_k = sk, ep.split_stride = static_cast<long long>(slice);
+        ep.out_f32 = split->ws, ep.residual = nullptr;
+        split->used = sk, split->slice_stride = static_cast<long long>(slice);
+      }
+    }
+  }
 
 #define NT_GEMM_CASE(FMT, BNV) return launch_gemm<FMT, BNV>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)
   if (a.dtype == NT_BF16) {
@@ -339,5 +381,5 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream) {
 
 extern "C" int nt_gemm(const nt_gemm_args* args, void* stream) {
   if (!args) return nt::set_error(NT_ERR_INVALID, "nt_gemm: null args");
-  return nt::gemm_dispatch(*args, reinterpret_cast<cudaStream_t>(stream));
+  return nt::gemm_dispatch(*args, reinterpret_cast<cudaStream_t>(stream), nullptr);
 }

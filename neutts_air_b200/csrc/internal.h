@@ -42,7 +42,16 @@ int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, 
   return NT_OK;
 }
 
-int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream);
+// Optional split-K lease: when the GEMM accumulates in place (residual == out_f32) and has too few tiles to fill
+// the GPU, it writes `used` raw partial slices [used][M][ldc] into ws instead of touching out_f32; the caller
+// must fold them (x += slice 0 + slice 1 + ..., in that order) before x is read -- rmsnorm_rows does.
+struct SplitK {
+  float* ws;
+  size_t ws_floats;
+  int used;                // out: 1 = no split happened (normal epilogue ran)
+  long long slice_stride;  // out: floats between slices
+};
+int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split = nullptr);
 
 // workspace carving helper (256-byte aligned sub-allocations from a caller-owned buffer)
 struct Arena {

@@ -54,7 +54,8 @@ struct nt_lm {
   std::vector<const float*> ln1, bqkv, ln2;
   std::vector<const __nv_bfloat16*> wqkv, wo, wgu, wd;
   // workspace
-  float *h, *q, *attn, *act, *logits, *part_o, *part_ml, *cand_val, *inv_freq, *qkv, *h_last;
+  float *h, *q, *attn, *act, *logits, *part_o, *part_ml, *cand_val, *inv_freq, *qkv, *h_last, *splitk_ws;
+  size_t splitk_floats;
   int *counters, *cand_idx, *tok_seq, *tok_pos, *cu_dev, *last_rows, *iota;
   __nv_bfloat16 *xn, *attn_bf16, *act_bf16;
   // megakernel tables (device)
@@ -112,6 +113,8 @@ static size_t lm_carve(const nt_lm_config& c, void* ws, size_t bytes, F&& assign
     (L)->phase_tab = a.take<MegaPhase>(size_t(4) * c.n_layers + 1);                            \
     (L)->ptr_tab = a.take<const float*>(size_t(3) * c.n_layers);                               \
     (L)->gbar = a.take<unsigned>(256);                                                         \
+    (L)->splitk_floats = size_t(8) * 128 * H;                                                  \
+    (L)->splitk_ws = a.take<float>(size_t(8) * 128 * H);                                       \
   }
 
 static int lm_check_config(const nt_lm_config* c) {
@@ -312,8 +315,17 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
   const float scale_log2 = (1.0f / 8.0f) * 1.4426950408889634f;
   int rc;
   const int n_layers = lm->debug_layers >= 0 ? lm->debug_layers : c.n_layers;
+  // o_proj / down_proj accumulate into the residual stream; with few row tiles (batched decode, short prompts)
+  // they split K over grid.z into lm->splitk_ws and the RMSNorm that follows folds the slices into lm->h.
+  // The last layer's down_proj never splits: what follows it (gather / final norm) reads lm->h directly.
+  SplitK pend;
+  pend.ws = lm->splitk_ws, pend.ws_floats = lm->splitk_floats, pend.used = 1, pend.slice_stride = 0;
+  const bool allow_split = !env_flag("NT_NO_SPLITK");
   for (int l = 0; l < n_layers; ++l) {
-    if ((rc = launch_rmsnorm_rows(lm->h, lm->ln1[l], c.rms_eps, rows, H, nullptr, lm->xn, stream))) return rc;
+    if ((rc = launch_rmsnorm_rows(lm->h, lm->ln1[l], c.rms_eps, rows, H, nullptr, lm->xn, stream,
+                                  pend.used > 1 ? pend.ws : nullptr, pend.used > 1 ? pend.used : 0, pend.slice_stride)))
+      return rc;
+    pend.used = 1;
     nt_gemm_args a;
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = QN, a.K = H, a.A = lm->xn, a.lda = H, a.W = lm->wqkv[l], a.ldw = H;
@@ -337,8 +349,11 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = H, a.K = HD, a.A = lm->attn_bf16, a.lda = HD, a.W = lm->wo[l], a.ldw = HD;
     a.residual = lm->h, a.ldr = H, a.out_f32 = lm->h, a.ldc = H;
-    if ((rc = gemm_dispatch(a, stream))) return rc;
-    if ((rc = launch_rmsnorm_rows(lm->h, lm->ln2[l], c.rms_eps, rows, H, nullptr, lm->xn, stream))) return rc;
+    if ((rc = gemm_dispatch(a, stream, allow_split ? &pend : nullptr))) return rc;
+    if ((rc = launch_rmsnorm_rows(lm->h, lm->ln2[l], c.rms_eps, rows, H, nullptr, lm->xn, stream,
+                                  pend.used > 1 ? pend.ws : nullptr, pend.used > 1 ? pend.used : 0, pend.slice_stride)))
+      return rc;
+    pend.used = 1;
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = 2 * I, a.K = H, a.A = lm->xn, a.lda = H, a.W = lm->wgu[l], a.ldw = H;
     a.act = NT_ACT_SWIGLU, a.out_bf16 = lm->act_bf16, a.ldc = I;
@@ -346,7 +361,7 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = H, a.K = I, a.A = lm->act_bf16, a.lda = I, a.W = lm->wd[l], a.ldw = I;
     a.residual = lm->h, a.ldr = H, a.out_f32 = lm->h, a.ldc = H;
-    if ((rc = gemm_dispatch(a, stream))) return rc;
+    if ((rc = gemm_dispatch(a, stream, (allow_split && l + 1 < n_layers) ? &pend : nullptr))) return rc;
   }
   return NT_OK;
 }

@@ -234,27 +234,66 @@ int launch_embed_rows(const __nv_bfloat16* embed, const int32_t* ids, int T, int
 }
 
 // one warp per row; fp32 statistics; out = w * (x * rsqrt(mean(x^2)+eps))  (modeling_qwen2.py:258-263)
-__global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const float* x, const float* w, float eps, int rows, int cols,
-                                                           float* out_f32, __nv_bfloat16* out_bf16) {
+// 16-byte loads, eight of them in flight per lane (the scalar version spent 16 us per launch on load latency).
+// With `parts`: first folds the split-K slices of the preceding in-place GEMM into the residual stream,
+// x[row] += parts[0][row] + parts[1][row] + ... in slice order (so the sum is reproducible), and writes x back.
+__global__ void __launch_bounds__(256) rmsnorm_rows_kernel(float* x, const float* w, float eps, int rows, int cols,
+                                                           float* out_f32, __nv_bfloat16* out_bf16, const float* parts,
+                                                           int nparts, long long pstride) {
   pdl_launch_dependents();
   pdl_wait();
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
-  const float* xr = x + static_cast<long long>(row) * cols;
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<long long>(row) * cols);
+  const float4* wr = reinterpret_cast<const float4*>(w);
+  const int nvec = cols >> 2;  // cols % 4 == 0 (checked by the launcher)
   float ss = 0.f;
-  for (int i = lane; i < cols; i += 32) ss += xr[i] * xr[i];
+  for (int i0 = lane; i0 < nvec; i0 += 32 * 8) {
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = (i0 + 32 * j < nvec) ? xr[i0 + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nparts > 0) {
+      for (int z = 0; z < nparts; ++z) {
+        const float4* pr = reinterpret_cast<const float4*>(parts + z * pstride + static_cast<long long>(row) * cols);
+        float4 t[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = (i0 + 32 * j < nvec) ? __ldcg(pr + i0 + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j].x += t[j].x, v[j].y += t[j].y, v[j].z += t[j].z, v[j].w += t[j].w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (i0 + 32 * j < nvec) xr[i0 + 32 * j] = v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+  }
   ss = warp_sum(ss);
   const float sc = rsqrtf(ss / static_cast<float>(cols) + eps);
-  for (int i = lane; i < cols; i += 32) {
-    const float v = w[i] * (xr[i] * sc);
-    if (out_f32) out_f32[static_cast<long long>(row) * cols + i] = v;
-    if (out_bf16) out_bf16[static_cast<long long>(row) * cols + i] = __float2bfloat16(v);
+  for (int i0 = lane; i0 < nvec; i0 += 32 * 8) {
+    float4 v[8], g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (i0 + 32 * j < nvec) v[j] = xr[i0 + 32 * j], g[j] = wr[i0 + 32 * j];   // x: this lane's own writes above
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + 32 * j;
+      if (i < nvec) {
+        const float4 o = make_float4(g[j].x * (v[j].x * sc), g[j].y * (v[j].y * sc), g[j].z * (v[j].z * sc), g[j].w * (v[j].w * sc));
+        if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * cols)[i] = o;
+        if (out_bf16)
+          reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * cols)[i] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+      }
+    }
   }
 }
 int launch_rmsnorm_rows(const float* x, const float* w, float eps, int rows, int cols, float* out_f32,
-                        __nv_bfloat16* out_bf16, cudaStream_t s) {
-  return launch_kernel(rmsnorm_rows_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, true, x, w, eps, rows, cols, out_f32,
-                       out_bf16);
+                        __nv_bfloat16* out_bf16, cudaStream_t s, const float* parts, int nparts, long long pstride) {
+  if (cols % 4) return set_error(NT_ERR_INVALID, "rmsnorm: cols must be a multiple of 4");
+  // few rows (batched decode): one warp per CTA so the rows spread over the SMs; many rows (prefill): 8 per CTA
+  const int wpc = rows >= 2048 ? 8 : (rows >= 512 ? 2 : 1);
+  return launch_kernel(rmsnorm_rows_kernel, dim3((rows + wpc - 1) / wpc), dim3(32 * wpc), 0, s, true, const_cast<float*>(x), w, eps,
+                       rows, cols, out_f32, out_bf16, parts, nparts, pstride);
 }
 
 // thread = one unit (pair of packed columns) of one token

@@ -97,8 +97,10 @@ size_t sampler_scratch_floats(int B, int V);  // per-array element count for can
 int sampler_nchunks(int V);
 
 int launch_embed_rows(const __nv_bfloat16* embed, const int32_t* ids, int T, int hidden, float* h, cudaStream_t s);
+// parts != nullptr: x is updated in place first (x += sum of nparts split-K slices, slice order) -- see SplitK
 int launch_rmsnorm_rows(const float* x, const float* w, float eps, int rows, int cols, float* out_f32,
-                        __nv_bfloat16* out_bf16, cudaStream_t s);
+                        __nv_bfloat16* out_bf16, cudaStream_t s, const float* parts = nullptr, int nparts = 0,
+                        long long pstride = 0);
 // qkv: [T, qkv_n] fp32 in packed (pair-interleaved) column order -> q natural order + K/V pages
 int launch_rope_append(const float* qkv, int T, int qkv_n, const int32_t* tok_seq, const int32_t* tok_pos, int n_heads,
                        const float* inv_freq, float* q_out, const KVLayout& kv, int layer, cudaStream_t s);

@@ -120,6 +120,10 @@ def test_lm_batched_decode(cuda, B):
         _, ref = O.generate(cfg, w, p, eos, max_length=256, max_new_tokens=n_new, forced=forced[b], mirror=False)
         assert rel_err(got[b], ref) < 2e-2 and max_err(got[b], ref) < 1e-1 * float(ref.std()), (b, rel_err(got[b], ref))
     assert lm.out_tokens[:B, :n_new].cpu().tolist() == forced.tolist()
+    # run-to-run reproducibility, bit for bit: concurrent instances and the split-K GEMMs (slices folded in
+    # slice order by the following RMSNorm) must not introduce order-dependent sums
+    again = _teacher_forced(cfg, w, lm, [p.tolist() for p in prompts], forced, n_new, eos)
+    assert torch.equal(got, again)
 
 
 def test_lm_generate_stops_and_graph_replay(cuda):

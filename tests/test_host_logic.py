@@ -265,3 +265,94 @@ def test_shard_plan_is_a_balanced_partition():
         assert max(len(p) for p in plan) - min(len(p) for p in plan) <= 1
     loads = [sum(lens[i] for i in p) for p in dist.shard_plan(len(lens), lens, 2)]
     assert max(loads) / min(loads) < 1.25
+
+
+class FakeStreamLM:
+    """prefill()/decode() surface of SpeechLM with a scripted token stream (speech ids, junk ids, EOS)."""
+    device = torch.device("cpu")
+
+    def __init__(self, script, max_new=4096):
+        self.script, self.max_new = list(script), max_new
+        self.out_tokens = torch.zeros(1, max_new, dtype=torch.int32)
+        self.n_generated = torch.zeros(1, dtype=torch.int32)
+        self.done = torch.zeros(1, dtype=torch.int32)
+        self.decode_calls = []
+
+    def sampling(self, eos, min_new, max_new, top_k, temperature, seed):
+        self.eos, self.limit = eos, max_new
+        return None
+
+    def _emit(self):
+        n = int(self.n_generated[0])
+        if int(self.done[0]) or n >= self.limit:
+            return
+        tok = self.script[n] if n < len(self.script) else self.eos
+        self.out_tokens[0, n] = tok
+        self.n_generated[0] = n + 1
+        if tok == self.eos or n + 1 >= self.limit:
+            self.done[0] = 1
+
+    def prefill(self, prompts, sp):
+        self._emit()
+
+    def decode(self, steps, sp):
+        assert steps >= 1
+        self.decode_calls.append(steps)
+        for _ in range(steps):
+            self._emit()
+
+
+class RampCodec:
+    """Deterministic 'codec': frame i of the window becomes hop samples of code/1000 + 0.01 * position-in-window,
+    so a wrong window start, slice or cross-fade weight changes the output."""
+    device = torch.device("cpu")
+    max_batch = 1
+    hop = 8
+
+    def decode_code(self, codes):
+        c = codes[0, 0].float()
+        frames = c[:, None] / 1000.0 + 0.01 * torch.arange(len(c))[:, None] + torch.zeros(1, self.hop)
+        return frames.reshape(1, 1, -1)
+
+
+@pytest.mark.parametrize("n_gen,junk_every,limit", [(143, 0, None), (90, 7, None), (30, 0, None), (12, 3, None), (400, 5, 301)])
+def test_stream_matches_reference_window_plan(n_gen, junk_every, limit):
+    """infer_stream == the reference's window bookkeeping (neutts/neutts.py:373-465) restated in
+    oracle/stream_oracle.py: same codec windows, same slices, same triangular cross-fade, including the
+    ragged tail, non-speech ids interleaved in the stream, and a stop by max_length instead of EOS."""
+    tts, tok = _tts()
+    codec = RampCodec()
+    hop = codec.hop
+    tts.codec, tts.hop_length = codec, hop
+    tts.streaming_stride_samples = tts.streaming_frames_per_chunk * hop
+    rng = np.random.default_rng(n_gen)
+    gen_codes = rng.integers(0, 65536, n_gen).tolist()
+    script = []
+    for i, c in enumerate(gen_codes):
+        if junk_every and i % junk_every == 0:
+            script.append(65)                       # a text token in the middle of speech: dropped
+        script.append(tok.speech_base + c)
+    lm = FakeStreamLM(script)
+    tts.backbone = lm
+    ref_codes = rng.integers(0, 65536, 60).tolist()
+    if limit is not None:
+        prompt_len = len(tts._apply_chat_template(ref_codes, "ref", "hello"))
+        tts.max_context = prompt_len + limit
+        kept = [t - tok.speech_base for t in script[:limit] if t >= tok.speech_base]
+    else:
+        kept = gen_codes
+    chunks = list(tts.infer_stream("hello", ref_codes, "ref"))
+    if limit is not None:
+        assert int(lm.n_generated[0]) == limit      # stopped by max_length, not EOS
+    # expected: decode every planned window with the same codec, slice, overlap-add
+    allc = ref_codes + kept
+    frames = []
+    for (t0, t1, s0, s1) in SO.chunk_plan(len(ref_codes), len(allc), hop=hop):
+        wav = codec.decode_code(torch.tensor(allc[t0:t1])[None, None, :])[0, 0].numpy()
+        frames.append(wav[s0:s1] if s1 is not None else wav[max(s0, 0):])
+    want = SO.linear_overlap_add(frames, tts.streaming_stride_samples) if frames else np.zeros(0, np.float32)
+    got = np.concatenate(chunks) if chunks else np.zeros(0, np.float32)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 1e-5
+    assert all(len(c) == tts.streaming_stride_samples for c in chunks[:-1])
+    assert max(lm.decode_calls, default=0) <= tts.streaming_frames_per_chunk + tts.streaming_lookforward
