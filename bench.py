@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="utterances per GPU per step (metric is quoted at 1, 8, 64)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sweep", action="store_true", help="also report batch 8 and 64 on this GPU under 'batches'")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the batch 8 / 64 lines reported under 'batches' (N=1 runs only)")
     return ap.parse_args()
 
 
@@ -201,16 +201,59 @@ def main_reference(args):
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
+_WEIGHTS = {}
+
+
 def build_engines(device, batch):
     from neutts_air_b200 import synthetic
     from neutts_air_b200.codec import CodecDecoder, CodecShape
     from neutts_air_b200.lm import LMShape, SpeechLM
 
     shape = LMShape()
-    lm = SpeechLM(shape, synthetic.lm_state_dict(shape, 0), device=device, max_batch=batch, max_ctx=2048, max_new=256,
+    if not _WEIGHTS:   # seeded random weights are generated once per process and shared by the sweep engines
+        _WEIGHTS["lm"] = synthetic.lm_state_dict(shape, 0)
+        _WEIGHTS["codec"] = synthetic.codec_weights(CodecShape(), 0)
+    lm = SpeechLM(shape, _WEIGHTS["lm"], device=device, max_batch=batch, max_ctx=2048, max_new=256,
                   max_prefill_tokens=batch * PREFILL)
-    codec = CodecDecoder(CodecShape(), synthetic.codec_weights(CodecShape(), 0), device=device, max_batch=batch, max_frames=256)
+    codec = CodecDecoder(CodecShape(), _WEIGHTS["codec"], device=device, max_batch=batch, max_frames=256)
     return lm, codec
+
+
+def quick_batch(dev, B, steps=2):
+    """One extra line of the metric at another batch size on this GPU (the metric is quoted at batch 1, 8 and 64):
+    same workload per utterance, inputs resident in HBM, CUDA-event timing, 1 warm-up + `steps` timed passes."""
+    lm, codec = build_engines(dev, B)
+    speech_base, eos = 151936, 151670
+    prompts = synth_prompts(B, lm.shape.vocab_size, speech_base, 4321)
+
+    def step(seed):
+        sp = lm.sampling(eos, min_new_tokens=DECODE, max_new_tokens=DECODE, top_k=50, temperature=1.0, seed=seed)
+        lm.prefill(prompts, sp)
+        lm.decode(DECODE - 1, sp)
+        c = (lm.out_tokens[:B, :DECODE].long() - speech_base).clamp_(0, 65535)[:, None, :]
+        return codec.decode_code(c)
+
+    step(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(10 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / 1e3 / steps
+    sp = lm.sampling(eos, min_new_tokens=DECODE, max_new_tokens=DECODE, seed=5)
+    lm.prefill(prompts, sp)
+    torch.cuda.synchronize()
+    e0.record()
+    lm.decode(DECODE - 1, sp)
+    e1.record()
+    torch.cuda.synchronize()
+    t_dec = e0.elapsed_time(e1) / 1e3
+    del lm, codec
+    torch.cuda.empty_cache()
+    return {"per_gpu_batch": B, "value": AUDIO_S * B / t, "unit": "audio-s/s", "ms_per_step": t * 1e3, "steps": steps,
+            "decode_tok_s": B * (DECODE - 1) / t_dec, "decode_ms_per_token_step": t_dec / (DECODE - 1) * 1e3}
 
 
 def main_b200(args):
@@ -335,8 +378,9 @@ def main_b200(args):
         alg = lm.shape.vocab_size * lm.shape.hidden_size * 2 + B * (lm.shape.hidden_size * 4 + lm.shape.vocab_size * 4)
         peak, how = peaks()
         roof = {"bound": "hbm", "kernel": "gemv_kernel<lm_head>", "achieved": alg / t_k / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg / t_k / 1e9 / peak, "traffic": None, "peak_source": how, "us_per_launch": t_k * 1e6,
-                "algorithmic_bytes": alg}
+                "frac": alg / t_k / 1e9 / peak, "traffic": 389.8e6 if B == 1 else None,
+                "traffic_source": "dram__bytes_read+write of one ncu --set full capture, profiles/head_gemv_r1_summary.txt",
+                "peak_source": how, "us_per_launch": t_k * 1e6, "algorithmic_bytes": alg}
 
     times = torch.tensor([t_dev, t_e2e, t_dec, t_pre, t_codec], device=dev, dtype=torch.float64)
     if world > 1:
@@ -373,6 +417,10 @@ def main_b200(args):
     }
     if roof:
         line["roofline"] = roof
+    if world == 1 and not args.no_sweep:
+        del lm, codec
+        torch.cuda.empty_cache()
+        line["batches"] = [quick_batch(dev, b) for b in (8, 64) if b != B]
     if not args.no_cpu_baseline and world == 1:
         try:
             v, ms, sample, cores, parts = reference_measure(1, 0)

@@ -360,7 +360,7 @@ struct CodecRun {
     a.N = Nout, a.K = K, a.A = A, a.lda = lda, a.W = W, a.ldw = K;
     a.bias = bias, a.residual = residual, a.ldr = ldc, a.act = act, a.out_f32 = out, a.ldc = ldc;
     if (masked) a.valid_period = Tp, a.valid_len = N;
-    return gemm_dispatch(a, s);
+    return gemm_dispatch(a, s, nullptr, true);
   }
   int resnet(int idx) {
     const nt_codec_config& c = k->cfg;
@@ -439,7 +439,7 @@ extern "C" int nt_codec_decode(nt_codec* k, const int32_t* codes, int B, int N, 
     memset(&a, 0, sizeof(a));
     a.dtype = NT_TF32, a.M = rows, a.N = c.n_fft, a.K = 2 * nb, a.A = k->sp, a.lda = kp, a.W = k->w.idft_basis, a.ldw = kp;
     a.out_f32 = k->fr, a.ldc = c.n_fft;
-    if ((rc = gemm_dispatch(a, s))) return rc;
+    if ((rc = gemm_dispatch(a, s, nullptr, true))) return rc;
   }
   return launch_kernel(ola_kernel, dim3((c.hop * N + 255) / 256, B), dim3(256), 0, s, true, (const float*)k->fr, N, Tp, c.n_fft, c.hop, pcm);
 }

@@ -28,23 +28,26 @@ struct GemmEpilogue {
   int valid_period, valid_len;
   int split_k;             // > 1: grid.z K-slices; slice z stores its raw partial sums at out_f32 + z * split_stride
   long long split_stride;  // (no residual / activation; bias rides on slice 0) -- the consumer adds them in z order
+  int w_const;             // W is never written on the device: its first ring of tiles may load before the PDL wait
 };
 
-template <int BN>
+// kShallow: half-depth ring (<= 113 KB) so two CTAs share an SM -- used when the grid is between one and two
+// waves of single-occupancy CTAs (e.g. gate/up at batched decode: 152 tiles on 148 SMs would take two rounds).
+template <int BN, bool kShallow = false>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN <= 64) ? 8 : (BN == 128 ? 6 : 4);
+  static constexpr int STAGES = kShallow ? (BN <= 64 ? 4 : 3) : ((BN <= 64) ? 8 : (BN == 128 ? 6 : 4));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int kFmt, int BN>
+template <int kFmt, int BN, bool kShallow>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep, int M,
                int N, int num_kb, int kb_per_tap) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kShallow>;
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BK_ELEMS = (kFmt == 2) ? 32 : 64;  // 128 bytes along K
 
@@ -84,6 +87,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Programmatic dependent launch: let the next kernel's CTAs start their prologue now (they block in their own
+  // griddepcontrol.wait until this grid has completed), and start streaming this kernel's weights -- which no
+  // kernel ever writes -- while the previous kernel is still finishing.
+  pdl_launch_dependents();
+  const int early = ep.w_const ? min(STAGES, kb_hi - kb_lo) : 0;
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < early; ++i) {
+      mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+      tma_load_2d(tiles + i * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, (kb_lo + i) * BK_ELEMS, n0, &full_bar[i]);
+    }
+  }
   pdl_wait();  // inputs (A, residual) may come from the previous kernel in the stream
 
   if (warp == 0) {
@@ -92,14 +106,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = kb_lo; kb < kb_hi; ++kb) {
         const int s = (kb - kb_lo) % STAGES;
         const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        const bool b_in_flight = (kb - kb_lo) < early;
+        if (!b_in_flight) {
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        }
         uint8_t* sa = tiles + s * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
         const int tap = kb / kb_per_tap;
         const int acol = (kb - tap * kb_per_tap) * BK_ELEMS;
         tma_load_2d(sa, &tmA, acol, m0 + tap, &full_bar[s]);
-        tma_load_2d(sb, &tmB, kb * BK_ELEMS, n0, &full_bar[s]);
+        if (!b_in_flight) tma_load_2d(sb, &tmB, kb * BK_ELEMS, n0, &full_bar[s]);
       }
     }
   } else if (warp == 1) {
@@ -237,7 +254,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   }
-  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, BN);
@@ -279,13 +295,13 @@ static int make_tmap(CUtensorMap* out, nt_dtype dt, const void* base, uint64_t r
   return NT_OK;
 }
 
-template <int kFmt, int BN>
+template <int kFmt, int BN, bool kShallow>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int num_kb,
                        int kb_per_tap, cudaStream_t stream) {
   const int splits = ep.split_k > 1 ? ep.split_k : 1;
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, kShallow>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<kFmt, BN>;
+  auto kern = gemm_tc_kernel<kFmt, BN, kShallow>;
   if (!attr_set) {
     NT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
@@ -295,7 +311,17 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
                        kb_per_tap);
 }
 
-int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split) {
+static int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, bool w_const) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error(NT_ERR_INVALID, "gemm: empty problem");
   const int esz = a.dtype == NT_BF16 ? 2 : 4;
   const int bk = 128 / esz;
@@ -347,6 +373,7 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split) {
   // SMs idle, so grid.z slices of the K loop store raw partial sums; the summation order stays fixed (z order)
   ep.split_k = 1;
   ep.split_stride = 0;
+  ep.w_const = w_const ? 1 : 0;
   if (split) {
     split->used = 1;
     const int tiles = mt * ((a.N + bn - 1) / bn);
@@ -364,7 +391,11 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split) {
     }
   }
 
-#define NT_GEMM_CASE(FMT, BNV) return launch_gemm<FMT, BNV>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)
+  const int ctas = mt * ((a.N + bn - 1) / bn) * (ep.split_k > 1 ? ep.split_k : 1);
+  const bool shallow = ctas > num_sms() && ctas <= 2 * num_sms();
+#define NT_GEMM_CASE(FMT, BNV)                                                                           \
+  return shallow ? launch_gemm<FMT, BNV, true>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)         \
+                 : launch_gemm<FMT, BNV, false>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)
   if (a.dtype == NT_BF16) {
     if (bn == 128) NT_GEMM_CASE(1, 128);
     if (bn == 64) NT_GEMM_CASE(1, 64);
@@ -381,5 +412,5 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split) {
 
 extern "C" int nt_gemm(const nt_gemm_args* args, void* stream) {
   if (!args) return nt::set_error(NT_ERR_INVALID, "nt_gemm: null args");
-  return nt::gemm_dispatch(*args, reinterpret_cast<cudaStream_t>(stream), nullptr);
+  return nt::gemm_dispatch(*args, reinterpret_cast<cudaStream_t>(stream), nullptr, /*w_const=*/false);
 }

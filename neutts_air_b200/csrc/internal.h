@@ -51,7 +51,8 @@ struct SplitK {
   int used;                // out: 1 = no split happened (normal epilogue ran)
   long long slice_stride;  // out: floats between slices
 };
-int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split = nullptr);
+// w_const: W holds model weights that no kernel writes, so the kernel may fetch them ahead of the PDL dependency
+int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split = nullptr, bool w_const = false);
 
 // workspace carving helper (256-byte aligned sub-allocations from a caller-owned buffer)
 struct Arena {

@@ -303,7 +303,7 @@ static int lm_head_rows(nt_lm* lm, const float* hrows, int B, float* logits, cud
   a.dtype = NT_BF16, a.M = B, a.N = c.vocab_size, a.K = c.hidden;
   a.A = lm->xn, a.lda = c.hidden, a.W = lm->lm_head, a.ldw = c.hidden;
   a.out_f32 = logits, a.ldc = c.vocab_size;
-  return gemm_dispatch(a, stream);
+  return gemm_dispatch(a, stream, nullptr, true);
 }
 
 // Transformer layers over `rows` token rows held in lm->h, via tensor-core GEMMs.
@@ -330,7 +330,7 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = QN, a.K = H, a.A = lm->xn, a.lda = H, a.W = lm->wqkv[l], a.ldw = H;
     a.bias = lm->bqkv[l], a.out_f32 = lm->qkv, a.ldc = QN;
-    if ((rc = gemm_dispatch(a, stream))) return rc;
+    if ((rc = gemm_dispatch(a, stream, nullptr, true))) return rc;
     const int32_t* tseq = mode == 0 ? lm->tok_seq : lm->iota;
     const int32_t* tpos = mode == 0 ? lm->tok_pos : st->seq_lens;
     if ((rc = launch_rope_append(lm->qkv, rows, QN, tseq, tpos, c.n_heads, lm->inv_freq, lm->q, kv, l, stream))) return rc;
@@ -349,7 +349,7 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = H, a.K = HD, a.A = lm->attn_bf16, a.lda = HD, a.W = lm->wo[l], a.ldw = HD;
     a.residual = lm->h, a.ldr = H, a.out_f32 = lm->h, a.ldc = H;
-    if ((rc = gemm_dispatch(a, stream, allow_split ? &pend : nullptr))) return rc;
+    if ((rc = gemm_dispatch(a, stream, allow_split ? &pend : nullptr, true))) return rc;
     if ((rc = launch_rmsnorm_rows(lm->h, lm->ln2[l], c.rms_eps, rows, H, nullptr, lm->xn, stream,
                                   pend.used > 1 ? pend.ws : nullptr, pend.used > 1 ? pend.used : 0, pend.slice_stride)))
       return rc;
@@ -357,11 +357,11 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = 2 * I, a.K = H, a.A = lm->xn, a.lda = H, a.W = lm->wgu[l], a.ldw = H;
     a.act = NT_ACT_SWIGLU, a.out_bf16 = lm->act_bf16, a.ldc = I;
-    if ((rc = gemm_dispatch(a, stream))) return rc;
+    if ((rc = gemm_dispatch(a, stream, nullptr, true))) return rc;
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = H, a.K = I, a.A = lm->act_bf16, a.lda = I, a.W = lm->wd[l], a.ldw = I;
     a.residual = lm->h, a.ldr = H, a.out_f32 = lm->h, a.ldc = H;
-    if ((rc = gemm_dispatch(a, stream, (allow_split && l + 1 < n_layers) ? &pend : nullptr))) return rc;
+    if ((rc = gemm_dispatch(a, stream, (allow_split && l + 1 < n_layers) ? &pend : nullptr, true))) return rc;
   }
   return NT_OK;
 }

@@ -241,122 +241,11 @@ struct AttnSync {      // lives outside any aliased shared-memory region
   int last;
 };
 
-// One (sequence b, kv head, split) work item: a 64-token page of K and V staged by bulk copies,
-// fp32 scores / softmax partials / P.V, then the last-arriving item of (b, kv head) merges the splits.
+// A work item covers `pps` consecutive 64-token pages of one (sequence, kv head): K and V pages staged by bulk
+// copies, fp32 scores, an online softmax across pages, and a partial (m, l, unnormalised o) written per split.
+// The per-op kernel merges the partials in its last-arriving CTA; in the megakernel the consumer of the
+// attention output merges them itself (load_attn_merged), so that phase has no atomic / last-arriver chain.
 // sy->bar must be initialised (count 1) and sy->uses must count its completed phases.
-template <typename Sync>
-NT_DEVINL void attn_decode_item(const AttnDecParams& p, int b, int kvh, int split, int n_ctx, int nsplit, AttnSmem* sm, AttnSync* sy,
-                                Sync sync) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_rep = p.n_rep;
-  const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + split);
-  const uint32_t parity = sy->uses & 1;
-  sync();  // previous item's readers are done with the staging buffers; `uses` was read by everyone
-  if (tid == 0) {
-    // K/V rows of this step were written through the generic proxy (possibly by another CTA, ordered by
-    // the grid barrier); the bulk copy reads through the async proxy
-    asm volatile("fence.proxy.async;" ::: "memory");
-    mbar_arrive_expect_tx(&sy->bar, 2 * 8192);
-    bulk_g2s(sm->k, p.kv.page_ptr(p.layer, 0, page, kvh), 8192, &sy->bar);
-    bulk_g2s(sm->v, p.kv.page_ptr(p.layer, 1, page, kvh), 8192, &sy->bar);
-    sy->uses += 1;
-  }
-  for (int i = tid; i < n_rep * 64; i += kConsumerThreads)
-    sm->q[i >> 6][i & 63] = __ldcg(p.q + (static_cast<long long>(b) * p.n_heads + kvh * n_rep + (i >> 6)) * 64 + (i & 63));
-  sync();
-  mbar_wait(&sy->bar, parity);
-
-  {  // scores: thread = (token, quarter of the head dim)
-    const int tok = tid >> 2, part = tid & 3;
-    const uint4* kr = reinterpret_cast<const uint4*>(sm->k + tok * 64 + part * 16);
-    float kf[16];
-    {
-      float t[8];
-      bf16x8_to_f32(kr[0], t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) kf[j] = t[j];
-      bf16x8_to_f32(kr[1], t);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) kf[8 + j] = t[j];
-    }
-    const bool valid = (split * 64 + tok) < n_ctx;
-    for (int h = 0; h < n_rep; ++h) {
-      float d = 0.f;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) d += kf[j] * sm->q[h][part * 16 + j];
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      d += __shfl_xor_sync(0xffffffffu, d, 2);
-      if (part == 0) sm->s[h][tok] = valid ? d * p.scale_log2 : -INFINITY;
-    }
-  }
-  sync();
-  if (warp < n_rep) {  // per-head softmax partials (fp32, base-2 exponent with log2e folded into the scale)
-    const float s0 = sm->s[warp][lane], s1 = sm->s[warp][lane + 32];
-    const float m = warp_max(fmaxf(s0, s1));  // the first token of every live split is valid -> finite
-    const float p0 = exp2f(s0 - m), p1 = exp2f(s1 - m);
-    const float l = warp_sum(p0 + p1);
-    sm->s[warp][lane] = p0;
-    sm->s[warp][lane + 32] = p1;
-    if (lane == 0) sm->ml[warp][0] = m, sm->ml[warp][1] = l;
-  }
-  sync();
-  {  // P.V : thread = (dim, token group of 16)
-    const int d = tid & 63, g = tid >> 6;
-    float acc[8];
-#pragma unroll
-    for (int h = 0; h < 8; ++h) acc[h] = 0.f;
-    for (int t = g * 16; t < g * 16 + 16; ++t) {
-      const float v = __bfloat162float(sm->v[t * 64 + d]);
-#pragma unroll
-      for (int h = 0; h < 8; ++h)
-        if (h < n_rep) acc[h] += sm->s[h][t] * v;
-    }
-#pragma unroll
-    for (int h = 0; h < 8; ++h)
-      if (h < n_rep) sm->red[g][h][d] = acc[h];
-  }
-  sync();
-  for (int i = tid; i < n_rep * 64; i += kConsumerThreads) {
-    const int h = i >> 6, d = i & 63;
-    const float o = sm->red[0][h][d] + sm->red[1][h][d] + sm->red[2][h][d] + sm->red[3][h][d];
-    const long long hh = static_cast<long long>(b) * p.n_heads + kvh * n_rep + h;
-    p.part_o[(hh * p.max_splits + split) * 64 + d] = o;
-    if (d == 0) {
-      p.part_ml[(hh * p.max_splits + split) * 2 + 0] = sm->ml[h][0];
-      p.part_ml[(hh * p.max_splits + split) * 2 + 1] = sm->ml[h][1];
-    }
-  }
-  // last item of this (sequence, kv head) merges the splits in split order (deterministic)
-  __threadfence();
-  sync();
-  if (tid == 0) {
-    const int old = atomicAdd(&p.counters[b * p.kv.n_kv_heads + kvh], 1);
-    sy->last = (old == nsplit - 1);
-  }
-  sync();
-  if (!sy->last) return;
-  __threadfence();
-  for (int i = tid; i < n_rep * 64; i += kConsumerThreads) {
-    const int h = i >> 6, d = i & 63;
-    const long long hh = static_cast<long long>(b) * p.n_heads + kvh * n_rep + h;
-    float M = -INFINITY;
-    for (int s = 0; s < nsplit; ++s) M = fmaxf(M, __ldcg(&p.part_ml[(hh * p.max_splits + s) * 2]));
-    float L = 0.f, O = 0.f;
-    for (int s = 0; s < nsplit; ++s) {
-      const float w = exp2f(__ldcg(&p.part_ml[(hh * p.max_splits + s) * 2]) - M);
-      L += w * __ldcg(&p.part_ml[(hh * p.max_splits + s) * 2 + 1]);
-      O += w * __ldcg(&p.part_o[(hh * p.max_splits + s) * 64 + d]);
-    }
-    p.out[hh * 64 + d] = O / L;
-    if (p.out_bf16) p.out_bf16[hh * 64 + d] = __float2bfloat16(O / L);
-  }
-  if (tid == 0) p.counters[b * p.kv.n_kv_heads + kvh] = 0;
-}
-
-// ---- megakernel variant: an item covers `pps` consecutive pages of one (sequence, kv head) with an
-// online softmax across pages and only writes its partial (m, l, unnormalised o); the consumer of
-// the attention output merges the partials itself (load_attn_merged), so there is no atomic /
-// last-arriver chain in the attention phase.
 NT_DEVINL void attn_issue_page(const AttnDecParams& p, int b, int kvh, int page_idx, AttnSmem* sm, AttnSync* sy) {
   const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + page_idx);
   asm volatile("fence.proxy.async;" ::: "memory");  // K/V rows may have been written through the generic proxy

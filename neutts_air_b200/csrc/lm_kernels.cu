@@ -148,28 +148,142 @@ int launch_gemv(const GemvParams& p, int nb, int num_sms, cudaStream_t stream) {
 }
 
 // =================================================================================== decode attention
-// grid (max_splits, n_kv_heads, B), 256 threads.  One 64-token page of one KV head per CTA.
-__global__ void __launch_bounds__(256) attn_decode_kernel(const AttnDecParams p) {
-  __shared__ __align__(128) AttnSmem sm;
-  __shared__ __align__(8) AttnSync sy;
+// grid (n_kv_heads, B), 256 threads: one CTA per (sequence, kv head), no cross-CTA partials.  Each of the 8 warps
+// owns a 16 KB K/V staging buffer and walks pages warp, warp+8, ... on its own (bulk copy -> private mbarrier ->
+// fp32 scores -> online softmax -> P.V), so page loads of different warps overlap and nothing but the final
+// merge needs a CTA-wide barrier.  The 8 warp partials merge through shared memory in warp order.
+constexpr int kAttnWarps = 8;
+struct AttnWarpSmem {
+  __nv_bfloat16 k[kAttnWarps][64 * 64];
+  __nv_bfloat16 v[kAttnWarps][64 * 64];
+  float q[8][64];               // pre-scaled by softmax scale * log2(e)
+  float p[kAttnWarps][64][8];   // probabilities [token][head]
+  float o[kAttnWarps][8][64];   // per-warp unnormalised outputs
+  float ml[kAttnWarps][8][2];
+  uint64_t bar[kAttnWarps];
+};
+__global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(const AttnDecParams p) {
+  extern __shared__ uint8_t attn_raw[];
+  AttnWarpSmem* sm = reinterpret_cast<AttnWarpSmem*>((reinterpret_cast<uintptr_t>(attn_raw) + 127) & ~uintptr_t(127));
   pdl_launch_dependents();
   pdl_wait();
-  const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int kvh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_rep = p.n_rep;
   const int n_ctx = min(__ldcg(p.kv.seq_lens + b) + 1, p.kv.max_ctx);
-  const int nsplit = (n_ctx + 63) >> 6;
-  if (split >= nsplit) return;
-  if (threadIdx.x == 0) {
-    mbar_init(&sy.bar, 1);
+  const int npages = (n_ctx + 63) >> 6;
+  if (lane == 0) {
+    mbar_init(&sm->bar[warp], 1);
     fence_barrier_init();
-    sy.uses = 0;
+  }
+  for (int i = tid; i < n_rep * 64; i += 32 * kAttnWarps)
+    sm->q[i >> 6][i & 63] = p.scale_log2 * __ldcg(p.q + (static_cast<long long>(b) * p.n_heads + kvh * n_rep + (i >> 6)) * 64 + (i & 63));
+  __syncthreads();
+
+  float m[8], l[8], acc[8][2];
+#pragma unroll
+  for (int h = 0; h < 8; ++h) m[h] = -INFINITY, l[h] = 0.f, acc[h][0] = 0.f, acc[h][1] = 0.f;
+  uint32_t parity = 0;
+  const __nv_bfloat16* kb = sm->k[warp];
+  const __nv_bfloat16* vb = sm->v[warp];
+  for (int pg = warp; pg < npages; pg += kAttnWarps) {
+    if (lane == 0) {
+      const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + pg);
+      asm volatile("fence.proxy.async;" ::: "memory");
+      mbar_arrive_expect_tx(&sm->bar[warp], 2 * 8192);
+      bulk_g2s(sm->k[warp], p.kv.page_ptr(p.layer, 0, page, kvh), 8192, &sm->bar[warp]);
+      bulk_g2s(sm->v[warp], p.kv.page_ptr(p.layer, 1, page, kvh), 8192, &sm->bar[warp]);
+    }
+    mbar_wait(&sm->bar[warp], parity);
+    parity ^= 1;
+    // scores: lane = tokens (lane, lane + 32), full 64-dim dot products in registers (14 independent FMA
+    // chains, no shuffles).  Lanes walk the eight 16-byte chunks of their K rows in a rotated order
+    // (chunk c ^ (lane & 7)) so that the 8 lanes of a shared-memory phase hit 8 different bank groups.
+    float d0[8], d1[8];
+#pragma unroll
+    for (int h = 0; h < 8; ++h) d0[h] = 0.f, d1[h] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int ch = c ^ (lane & 7);
+      float f0[8], f1[8];
+      bf16x8_to_f32(*reinterpret_cast<const uint4*>(kb + lane * 64 + ch * 8), f0);
+      bf16x8_to_f32(*reinterpret_cast<const uint4*>(kb + (lane + 32) * 64 + ch * 8), f1);
+#pragma unroll
+      for (int h = 0; h < 8; ++h) {
+        if (h < n_rep) {
+          const float4 qa = *reinterpret_cast<const float4*>(&sm->q[h][ch * 8]);
+          const float4 qb = *reinterpret_cast<const float4*>(&sm->q[h][ch * 8 + 4]);
+          d0[h] += f0[0] * qa.x + f0[1] * qa.y + f0[2] * qa.z + f0[3] * qa.w + f0[4] * qb.x + f0[5] * qb.y + f0[6] * qb.z + f0[7] * qb.w;
+          d1[h] += f1[0] * qa.x + f1[1] * qa.y + f1[2] * qa.z + f1[3] * qa.w + f1[4] * qb.x + f1[5] * qb.y + f1[6] * qb.z + f1[7] * qb.w;
+        }
+      }
+    }
+    // online softmax (fp32, base-2); running (m, l) replicated in every lane
+    const bool valid0 = (pg * 64 + lane) < n_ctx, valid1 = (pg * 64 + lane + 32) < n_ctx;
+#pragma unroll
+    for (int h = 0; h < 8; ++h) {
+      if (h < n_rep) {
+        const float s0 = valid0 ? d0[h] : -INFINITY, s1 = valid1 ? d1[h] : -INFINITY;
+        const float mn = fmaxf(m[h], warp_max(fmaxf(s0, s1)));  // every page walked has a valid token -> finite
+        d0[h] = exp2f(s0 - mn), d1[h] = exp2f(s1 - mn);
+        const float c = exp2f(m[h] - mn);                       // 0 on the warp's first page
+        l[h] = l[h] * c + warp_sum(d0[h] + d1[h]);
+        m[h] = mn;
+        acc[h][0] *= c, acc[h][1] *= c;
+      }
+    }
+    *reinterpret_cast<float4*>(&sm->p[warp][lane][0]) = make_float4(d0[0], d0[1], d0[2], d0[3]);
+    *reinterpret_cast<float4*>(&sm->p[warp][lane][4]) = make_float4(d0[4], d0[5], d0[6], d0[7]);
+    *reinterpret_cast<float4*>(&sm->p[warp][lane + 32][0]) = make_float4(d1[0], d1[1], d1[2], d1[3]);
+    *reinterpret_cast<float4*>(&sm->p[warp][lane + 32][4]) = make_float4(d1[4], d1[5], d1[6], d1[7]);
+    __syncwarp();
+    // P.V: lane = dims (2 lane, 2 lane + 1)
+#pragma unroll 8
+    for (int t = 0; t < 64; ++t) {
+      const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + t * 64 + 2 * lane));
+      const float4 pa = *reinterpret_cast<const float4*>(&sm->p[warp][t][0]);
+      const float4 pb = *reinterpret_cast<const float4*>(&sm->p[warp][t][4]);
+      const float pr[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+#pragma unroll
+      for (int h = 0; h < 8; ++h)
+        if (h < n_rep) acc[h][0] += pr[h] * vv.x, acc[h][1] += pr[h] * vv.y;
+    }
+    __syncwarp();  // the next bulk copy overwrites this warp's K/V buffers
+  }
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    if (h < n_rep) {
+      *reinterpret_cast<float2*>(&sm->o[warp][h][2 * lane]) = make_float2(acc[h][0], acc[h][1]);
+      if (lane == 0) sm->ml[warp][h][0] = m[h], sm->ml[warp][h][1] = l[h];
+    }
   }
   __syncthreads();
-  attn_decode_item(p, b, kvh, split, n_ctx, nsplit, &sm, &sy, SyncAll());
+  for (int i = tid; i < n_rep * 64; i += 32 * kAttnWarps) {
+    const int h = i >> 6, d = i & 63;
+    float M = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) M = fmaxf(M, sm->ml[w][h][0]);
+    float L = 0.f, O = 0.f;
+#pragma unroll
+    for (int w = 0; w < kAttnWarps; ++w) {
+      const float wgt = exp2f(sm->ml[w][h][0] - M);  // 0 for a warp that walked no page (m = -inf, l = 0)
+      L += wgt * sm->ml[w][h][1];
+      O += wgt * sm->o[w][h][d];
+    }
+    const long long hh = static_cast<long long>(b) * p.n_heads + kvh * n_rep + h;
+    if (p.out) p.out[hh * 64 + d] = O / L;
+    if (p.out_bf16) p.out_bf16[hh * 64 + d] = __float2bfloat16(O / L);
+  }
 }
 
 int launch_attn_decode(const AttnDecParams& p, int B, cudaStream_t stream) {
   if (p.n_rep < 1 || p.n_rep > 8) return set_error(NT_ERR_INVALID, "attention: %d query heads per KV head unsupported (1..8)", p.n_rep);
-  return launch_kernel(attn_decode_kernel, dim3(p.max_splits, p.kv.n_kv_heads, B), dim3(256), 0, stream, true, p);
+  static bool attr_set = false;
+  const int smem = int(sizeof(AttnWarpSmem)) + 128;
+  if (!attr_set) {
+    NT_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  return launch_kernel(attn_decode_kernel, dim3(p.kv.n_kv_heads, B), dim3(32 * kAttnWarps), smem, stream, true, p);
 }
 
 // =================================================================================== sampler
