@@ -279,7 +279,7 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 }
 
 // rows x cols (elements) matrix with row stride ld (elements); box = box_rows x 128 bytes.
-static int make_tmap(CUtensorMap* out, nt_dtype dt, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+int make_tmap(CUtensorMap* out, nt_dtype dt, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows) {
   PFN_tmapEncodeTiled fn = get_encode_fn();
   if (!fn) return set_error(NT_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");

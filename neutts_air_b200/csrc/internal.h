@@ -8,11 +8,16 @@
 
 #include "../../include/neutts_b200.h"
 
+struct CUtensorMap_st;  // <cuda.h>
+
 namespace nt {
 
 int set_error(int code, const char* fmt, ...);
 extern std::atomic<uint64_t> g_launches;
 bool pdl_disabled();  // NT_NO_PDL=1: launch without the programmatic-dependent-launch attribute (experiments)
+// Every kernel of the library asks for the maximum shared-memory carveout, so consecutive kernels never force the
+// SM to switch its L1 / shared-memory split (the big-tile kernels need ~180 KB; the small ones do not use L1 much).
+void prefer_max_smem_carveout(const void* kernel);
 
 #define NT_CUDA_CHECK(expr)                                                                          \
   do {                                                                                               \
@@ -26,6 +31,7 @@ bool pdl_disabled();  // NT_NO_PDL=1: launch without the programmatic-dependent-
 template <typename... KArgs, typename... Args>
 int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
                   Args&&... args) {
+  prefer_max_smem_carveout(reinterpret_cast<const void*>(kernel));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -53,6 +59,10 @@ struct SplitK {
 };
 // w_const: W holds model weights that no kernel writes, so the kernel may fetch them ahead of the PDL dependency
 int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split = nullptr, bool w_const = false);
+
+// 2-D TMA descriptor over a row-major matrix (rows x cols elements, row stride ld elements); box = box_rows x 128
+// bytes, SWIZZLE_128B (gemm_tc.cu)
+int make_tmap(::CUtensorMap_st* out, nt_dtype dt, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 // workspace carving helper (256-byte aligned sub-allocations from a caller-owned buffer)
 struct Arena {

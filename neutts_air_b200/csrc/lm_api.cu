@@ -29,6 +29,23 @@ static bool env_flag(const char* name) {
   const char* v = getenv(name);
   return v && v[0] && v[0] != '0';
 }
+// largest batch the persistent decode megakernel takes (default 4; up to 16 via concurrent instances)
+static int mega_max_batch() {
+  const char* e = getenv("NT_MEGA_MAX_BATCH");
+  const int n = e ? atoi(e) : 4;
+  return n < 1 ? 1 : (n > 16 ? 16 : n);
+}
+void prefer_max_smem_carveout(const void* kernel) {
+  static const bool off = env_flag("NT_NO_CARVEOUT");
+  if (off) return;
+  static std::mutex mu;
+  static std::vector<const void*> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  for (const void* k : seen)
+    if (k == kernel) return;
+  seen.push_back(kernel);
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 bool pdl_disabled() {
   static const bool off = env_flag("NT_NO_PDL");
   return off;
@@ -285,7 +302,7 @@ static int check_sampling(const nt_lm* lm, const nt_lm_state* st, const nt_sampl
 }
 
 // lm_head on B hidden rows (fp32, un-normalised) -> lm->logits / `logits`
-static int lm_head_rows(nt_lm* lm, const float* hrows, int B, float* logits, cudaStream_t stream) {
+static int lm_head_rows(nt_lm* lm, const float* hrows, int B, float* logits, cudaStream_t stream, const SplitK* pend = nullptr) {
   const nt_lm_config& c = lm->cfg;
   if (B <= 4) {
     GemvParams g;
@@ -296,7 +313,11 @@ static int lm_head_rows(nt_lm* lm, const float* hrows, int B, float* logits, cud
     g.epi = GEMV_STORE, g.out = logits, g.ldo = c.vocab_size;
     return launch_gemv(g, B, lm->num_sms, stream);
   }
-  int rc = launch_rmsnorm_rows(hrows, lm->final_norm, c.rms_eps, B, c.hidden, nullptr, lm->xn, stream);
+  // pend: the last down_proj left split-K slices that still have to be folded into hrows (batched decode only)
+  const bool fold = pend && pend->used > 1;
+  if (fold && B <= 4) return set_error(NT_ERR_STATE, "lm_head: pending split-K slices on the GEMV path");
+  int rc = launch_rmsnorm_rows(hrows, lm->final_norm, c.rms_eps, B, c.hidden, nullptr, lm->xn, stream, fold ? pend->ws : nullptr,
+                               fold ? pend->used : 0, fold ? pend->slice_stride : 0);
   if (rc) return rc;
   nt_gemm_args a;
   memset(&a, 0, sizeof(a));
@@ -308,7 +329,8 @@ static int lm_head_rows(nt_lm* lm, const float* hrows, int B, float* logits, cud
 
 // Transformer layers over `rows` token rows held in lm->h, via tensor-core GEMMs.
 // mode 0: prefill (causal attention over the prompt);  mode 1: one new token per sequence.
-static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mode, int max_len, cudaStream_t stream) {
+static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mode, int max_len, cudaStream_t stream,
+                       SplitK* tail = nullptr) {
   const nt_lm_config& c = lm->cfg;
   const KVLayout kv = make_kv(lm, st);
   const int H = c.hidden, I = c.inter, QN = lm->qkv_n, HD = c.n_heads * 64;
@@ -317,7 +339,8 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
   const int n_layers = lm->debug_layers >= 0 ? lm->debug_layers : c.n_layers;
   // o_proj / down_proj accumulate into the residual stream; with few row tiles (batched decode, short prompts)
   // they split K over grid.z into lm->splitk_ws and the RMSNorm that follows folds the slices into lm->h.
-  // The last layer's down_proj never splits: what follows it (gather / final norm) reads lm->h directly.
+  // The last layer's down_proj splits only when the caller takes over the fold (`tail`: decode, where the final
+  // norm of lm_head_rows reads lm->h next); in prefill a row gather comes first, so it stays whole.
   SplitK pend;
   pend.ws = lm->splitk_ws, pend.ws_floats = lm->splitk_floats, pend.used = 1, pend.slice_stride = 0;
   const bool allow_split = !env_flag("NT_NO_SPLITK");
@@ -344,7 +367,7 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
       ad.q = lm->q, ad.kv = kv, ad.layer = l, ad.n_heads = c.n_heads, ad.n_rep = c.n_heads / c.n_kv_heads;
       ad.scale_log2 = scale_log2, ad.part_o = lm->part_o, ad.part_ml = lm->part_ml, ad.counters = lm->counters;
       ad.out = lm->attn, ad.out_bf16 = lm->attn_bf16, ad.max_splits = lm->max_splits;
-      if ((rc = launch_attn_decode(ad, B, stream))) return rc;
+      if ((rc = launch_attn_decode(ad, B, c.n_layers, stream))) return rc;
     }
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = H, a.K = HD, a.A = lm->attn_bf16, a.lda = HD, a.W = lm->wo[l], a.ldw = HD;
@@ -361,8 +384,9 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = H, a.K = I, a.A = lm->act_bf16, a.lda = I, a.W = lm->wd[l], a.ldw = I;
     a.residual = lm->h, a.ldr = H, a.out_f32 = lm->h, a.ldc = H;
-    if ((rc = gemm_dispatch(a, stream, (allow_split && l + 1 < n_layers) ? &pend : nullptr, true))) return rc;
+    if ((rc = gemm_dispatch(a, stream, (allow_split && (l + 1 < n_layers || tail)) ? &pend : nullptr, true))) return rc;
   }
+  if (tail) *tail = pend;
   return NT_OK;
 }
 
@@ -409,6 +433,8 @@ extern "C" int nt_lm_prefill(nt_lm* lm, const nt_lm_state* st, const int32_t* id
 static int decode_step(nt_lm* lm, const nt_lm_state* st, int B, const nt_sampling* sp, cudaStream_t stream) {
   const nt_lm_config& c = lm->cfg;
   int rc;
+  SplitK tail;
+  tail.ws = nullptr, tail.ws_floats = 0, tail.used = 1, tail.slice_stride = 0;
   if (B <= 4) {
     const KVLayout kv = make_kv(lm, st);
     const int H = c.hidden, I = c.inter, HD = c.n_heads * 64;
@@ -426,7 +452,7 @@ static int decode_step(nt_lm* lm, const nt_lm_state* st, int B, const nt_samplin
       ad.q = lm->q, ad.kv = kv, ad.layer = l, ad.n_heads = c.n_heads, ad.n_rep = c.n_heads / c.n_kv_heads;
       ad.scale_log2 = scale_log2, ad.part_o = lm->part_o, ad.part_ml = lm->part_ml, ad.counters = lm->counters;
       ad.out = lm->attn, ad.out_bf16 = nullptr, ad.max_splits = lm->max_splits;
-      if ((rc = launch_attn_decode(ad, B, stream))) return rc;
+      if ((rc = launch_attn_decode(ad, B, c.n_layers, stream))) return rc;
 
       memset(&g, 0, sizeof(g));
       g.W = lm->wo[l], g.rows = H, g.K = HD, g.x = lm->attn, g.ldx = HD;
@@ -445,9 +471,9 @@ static int decode_step(nt_lm* lm, const nt_lm_state* st, int B, const nt_samplin
       if ((rc = launch_gemv(g, B, lm->num_sms, stream))) return rc;
     }
   } else {
-    if ((rc = layers_gemm(lm, st, B, B, 1, 0, stream))) return rc;
+    if ((rc = layers_gemm(lm, st, B, B, 1, 0, stream, &tail))) return rc;
   }
-  if ((rc = lm_head_rows(lm, lm->h, B, lm->logits, stream))) return rc;
+  if ((rc = lm_head_rows(lm, lm->h, B, lm->logits, stream, &tail))) return rc;
   SamplerParams s = make_sampler(lm, st, sp);
   s.advance = 1;
   return launch_sampler(s, B, stream);
@@ -465,10 +491,11 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
   if (n_steps < 0) return set_error(NT_ERR_INVALID, "negative step count");
 
   if (n_steps == 0) return NT_OK;
-  if (B <= 16 && !env_flag("NT_NO_MEGA") && c.hidden % 64 == 0) {
+  if (B <= mega_max_batch() && !env_flag("NT_NO_MEGA") && c.hidden % 64 == 0) {
     // Persistent megakernel: every layer, the lm_head, the sampler and all n_steps in one launch.
-    // Batch 5..16 runs as up to four concurrent instances of <= 4 sequences on disjoint SM subsets
-    // (each streams the full weights; the decode step is latency-bound, HBM has the headroom).
+    // It wins up to 4 sequences (0.86 ms / step at batch 1 against 1.65 ms for the per-op chain, whose step time
+    // is the same from batch 5 to 64).  NT_MEGA_MAX_BATCH=5..16 instead runs up to four concurrent instances of
+    // <= 4 sequences on disjoint SM subsets (measured 1.78 ms at batch 8, 2.5 ms at 16: slower than per-op).
     const int ngroups = (B + 3) / 4;
     const int per = (B + ngroups - 1) / ngroups;
     const int sms = lm->num_sms / ngroups;

@@ -7,15 +7,18 @@
 //                      Fused epilogues: bias + RoPE + KV-page append (:217-225), residual add
 //                      (:302,:308), SiLU(gate)*up (:46-48).  The weight prefetch is issued
 //                      BEFORE griddepcontrol.wait so it overlaps the previous kernel (PDL).
-//   attn_decode_kernel split-KV GQA attention over 64-token pages staged by bulk copies;
-//                      fp32 softmax (:161-183); last-arriving CTA merges the splits.
+//   attn_decode_kernel GQA attention over 64-token pages (one CTA per sequence and KV head, warp pairs
+//                      walk the pages); fp32 online softmax (:161-183).
 //   topk kernels       min-new-tokens EOS mask, temperature, top-k, softmax, multinomial
 //                      (logits_process.py:224-233,296-299,580-586; utils.py:2789-2791).
 // Prefill helpers (the GEMMs go through gemm_tc.cu): embedding gather, RMSNorm rows,
 // RoPE + KV append, causal GQA attention.
 #include "lm_device.cuh"
 
+#include <cuda.h>
+
 #include <cfloat>
+#include <mutex>
 
 namespace nt {
 
@@ -148,33 +151,45 @@ int launch_gemv(const GemvParams& p, int nb, int num_sms, cudaStream_t stream) {
 }
 
 // =================================================================================== decode attention
-// grid (n_kv_heads, B), 256 threads: one CTA per (sequence, kv head), no cross-CTA partials.  Each of the 8 warps
-// owns a 16 KB K/V staging buffer and walks pages warp, warp+8, ... on its own (bulk copy -> private mbarrier ->
-// fp32 scores -> online softmax -> P.V), so page loads of different warps overlap and nothing but the final
-// merge needs a CTA-wide barrier.  The 8 warp partials merge through shared memory in warp order.
-constexpr int kAttnWarps = 8;
+// grid (n_kv_heads, B), 512 threads: one CTA per (sequence, kv head), no cross-CTA partials.  The 16 warps form
+// 8 pairs; each pair owns a 16 KB K/V staging buffer and walks pages pair, pair+8, ... on its own (TMA -> the
+// pair's mbarrier -> fp32 scores -> online softmax -> P.V; each warp takes 32 of the page's 64 tokens), so the
+// page loads of different pairs overlap and only the final merge needs a CTA-wide barrier.  The 16 warp partials
+// merge through shared memory in warp order.
+//
+// Shared-memory bandwidth is what bounds this kernel (ncu: 18.8 k wavefronts per CTA, 5-way "conflicts"), so the
+// layout is chosen to make every query read a whole-warp broadcast: lane = token, all lanes walk the same 16-byte
+// chunk c of their K rows at the same time, and the K page lands in shared memory through a SWIZZLE_128B tensor
+// map (chunk c of row r sits at chunk c ^ (r & 7)), which keeps those row-strided reads conflict-free.
+// (History: split-KV grid + last-arriver merge 29 us; 8 warps x whole pages 17 us; per-lane rotated chunk order
+// with non-broadcast query reads 21 us.)
+constexpr int kAttnPairs = 8;
+constexpr int kAttnWarps = 2 * kAttnPairs;
 struct AttnWarpSmem {
-  __nv_bfloat16 k[kAttnWarps][64 * 64];
-  __nv_bfloat16 v[kAttnWarps][64 * 64];
+  __nv_bfloat16 k[kAttnPairs][64 * 64];   // swizzled (TMA); each buffer 8 KB => 1024-byte aligned
+  __nv_bfloat16 v[kAttnPairs][64 * 64];   // linear (bulk copy)
   float q[8][64];               // pre-scaled by softmax scale * log2(e)
-  float p[kAttnWarps][64][8];   // probabilities [token][head]
+  float p[kAttnWarps][32][8];   // probabilities [token][head]
   float o[kAttnWarps][8][64];   // per-warp unnormalised outputs
   float ml[kAttnWarps][8][2];
-  uint64_t bar[kAttnWarps];
+  uint64_t bar[kAttnPairs];
 };
-__global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(const AttnDecParams p) {
+__global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(const AttnDecParams p, const __grid_constant__ CUtensorMap kmap) {
   extern __shared__ uint8_t attn_raw[];
-  AttnWarpSmem* sm = reinterpret_cast<AttnWarpSmem*>((reinterpret_cast<uintptr_t>(attn_raw) + 127) & ~uintptr_t(127));
+  // array + offset keeps the shared address space visible to the compiler (LDS, not generic loads)
+  AttnWarpSmem* sm = reinterpret_cast<AttnWarpSmem*>(attn_raw + ((1024u - (smem_u32(attn_raw) & 1023u)) & 1023u));
   pdl_launch_dependents();
-  pdl_wait();
   const int kvh = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pair = warp >> 1, sub = warp & 1;
   const int n_rep = p.n_rep;
-  const int n_ctx = min(__ldcg(p.kv.seq_lens + b) + 1, p.kv.max_ctx);
-  const int npages = (n_ctx + 63) >> 6;
-  if (lane == 0) {
-    mbar_init(&sm->bar[warp], 1);
+  if (sub == 0 && lane == 0) {
+    if (pair == 0) tma_prefetch_desc(&kmap);
+    mbar_init(&sm->bar[pair], 1);
     fence_barrier_init();
   }
+  pdl_wait();
+  const int n_ctx = min(__ldcg(p.kv.seq_lens + b) + 1, p.kv.max_ctx);
+  const int npages = (n_ctx + 63) >> 6;
   for (int i = tid; i < n_rep * 64; i += 32 * kAttnWarps)
     sm->q[i >> 6][i & 63] = p.scale_log2 * __ldcg(p.q + (static_cast<long long>(b) * p.n_heads + kvh * n_rep + (i >> 6)) * 64 + (i & 63));
   __syncthreads();
@@ -183,71 +198,68 @@ __global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(const Attn
 #pragma unroll
   for (int h = 0; h < 8; ++h) m[h] = -INFINITY, l[h] = 0.f, acc[h][0] = 0.f, acc[h][1] = 0.f;
   uint32_t parity = 0;
-  const __nv_bfloat16* kb = sm->k[warp];
-  const __nv_bfloat16* vb = sm->v[warp];
-  for (int pg = warp; pg < npages; pg += kAttnWarps) {
-    if (lane == 0) {
+  const __nv_bfloat16* kb = sm->k[pair] + (sub * 32 + lane) * 64;  // this lane's token row of the page
+  const __nv_bfloat16* vb = sm->v[pair] + sub * 32 * 64;           // this warp's 32 token rows
+  const int krow_layer = p.layer * 2 * p.kv.num_pages * p.kv.n_kv_heads * 64;  // K rows of this layer in the pool
+  for (int pg = pair; pg < npages; pg += kAttnPairs) {
+    if (sub == 0 && lane == 0) {
       const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + pg);
       asm volatile("fence.proxy.async;" ::: "memory");
-      mbar_arrive_expect_tx(&sm->bar[warp], 2 * 8192);
-      bulk_g2s(sm->k[warp], p.kv.page_ptr(p.layer, 0, page, kvh), 8192, &sm->bar[warp]);
-      bulk_g2s(sm->v[warp], p.kv.page_ptr(p.layer, 1, page, kvh), 8192, &sm->bar[warp]);
+      mbar_arrive_expect_tx(&sm->bar[pair], 2 * 8192);
+      tma_load_2d(sm->k[pair], &kmap, 0, krow_layer + (page * p.kv.n_kv_heads + kvh) * 64, &sm->bar[pair]);
+      bulk_g2s(sm->v[pair], p.kv.page_ptr(p.layer, 1, page, kvh), 8192, &sm->bar[pair]);
     }
-    mbar_wait(&sm->bar[warp], parity);
+    mbar_wait(&sm->bar[pair], parity);
     parity ^= 1;
-    // scores: lane = tokens (lane, lane + 32), full 64-dim dot products in registers (14 independent FMA
-    // chains, no shuffles).  Lanes walk the eight 16-byte chunks of their K rows in a rotated order
-    // (chunk c ^ (lane & 7)) so that the 8 lanes of a shared-memory phase hit 8 different bank groups.
-    float d0[8], d1[8];
+    const int tok0 = pg * 64 + sub * 32;
+    if (tok0 < n_ctx) {  // warp-uniform: the second half of the last page may be entirely beyond the context
+      float d[8];
 #pragma unroll
-    for (int h = 0; h < 8; ++h) d0[h] = 0.f, d1[h] = 0.f;
+      for (int h = 0; h < 8; ++h) d[h] = 0.f;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int ch = c ^ (lane & 7);
-      float f0[8], f1[8];
-      bf16x8_to_f32(*reinterpret_cast<const uint4*>(kb + lane * 64 + ch * 8), f0);
-      bf16x8_to_f32(*reinterpret_cast<const uint4*>(kb + (lane + 32) * 64 + ch * 8), f1);
+      for (int c = 0; c < 8; ++c) {
+        float f[8];
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(kb + ((c ^ (lane & 7)) << 3)), f);  // logical chunk c, swizzled
+#pragma unroll
+        for (int h = 0; h < 8; ++h) {
+          if (h < n_rep) {
+            const float4 qa = *reinterpret_cast<const float4*>(&sm->q[h][c * 8]);      // same address in all lanes
+            const float4 qb = *reinterpret_cast<const float4*>(&sm->q[h][c * 8 + 4]);
+            d[h] += f[0] * qa.x + f[1] * qa.y + f[2] * qa.z + f[3] * qa.w + f[4] * qb.x + f[5] * qb.y + f[6] * qb.z + f[7] * qb.w;
+          }
+        }
+      }
+      // online softmax (fp32, base-2); running (m, l) replicated in every lane
+      const bool valid = (tok0 + lane) < n_ctx;
 #pragma unroll
       for (int h = 0; h < 8; ++h) {
         if (h < n_rep) {
-          const float4 qa = *reinterpret_cast<const float4*>(&sm->q[h][ch * 8]);
-          const float4 qb = *reinterpret_cast<const float4*>(&sm->q[h][ch * 8 + 4]);
-          d0[h] += f0[0] * qa.x + f0[1] * qa.y + f0[2] * qa.z + f0[3] * qa.w + f0[4] * qb.x + f0[5] * qb.y + f0[6] * qb.z + f0[7] * qb.w;
-          d1[h] += f1[0] * qa.x + f1[1] * qa.y + f1[2] * qa.z + f1[3] * qa.w + f1[4] * qb.x + f1[5] * qb.y + f1[6] * qb.z + f1[7] * qb.w;
+          const float sc = valid ? d[h] : -INFINITY;
+          const float mn = fmaxf(m[h], warp_max(sc));   // token tok0 is valid -> finite
+          d[h] = exp2f(sc - mn);
+          const float c = exp2f(m[h] - mn);             // 0 on the warp's first page
+          l[h] = l[h] * c + warp_sum(d[h]);
+          m[h] = mn;
+          acc[h][0] *= c, acc[h][1] *= c;
         }
       }
-    }
-    // online softmax (fp32, base-2); running (m, l) replicated in every lane
-    const bool valid0 = (pg * 64 + lane) < n_ctx, valid1 = (pg * 64 + lane + 32) < n_ctx;
+      *reinterpret_cast<float4*>(&sm->p[warp][lane][0]) = make_float4(d[0], d[1], d[2], d[3]);
+      *reinterpret_cast<float4*>(&sm->p[warp][lane][4]) = make_float4(d[4], d[5], d[6], d[7]);
+      __syncwarp();
+      // P.V: lane = dims (2 lane, 2 lane + 1); probabilities are whole-warp broadcasts
+#pragma unroll 8
+      for (int t = 0; t < 32; ++t) {
+        const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + t * 64 + 2 * lane));
+        const float4 pa = *reinterpret_cast<const float4*>(&sm->p[warp][t][0]);
+        const float4 pb = *reinterpret_cast<const float4*>(&sm->p[warp][t][4]);
+        const float pr[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
-    for (int h = 0; h < 8; ++h) {
-      if (h < n_rep) {
-        const float s0 = valid0 ? d0[h] : -INFINITY, s1 = valid1 ? d1[h] : -INFINITY;
-        const float mn = fmaxf(m[h], warp_max(fmaxf(s0, s1)));  // every page walked has a valid token -> finite
-        d0[h] = exp2f(s0 - mn), d1[h] = exp2f(s1 - mn);
-        const float c = exp2f(m[h] - mn);                       // 0 on the warp's first page
-        l[h] = l[h] * c + warp_sum(d0[h] + d1[h]);
-        m[h] = mn;
-        acc[h][0] *= c, acc[h][1] *= c;
+        for (int h = 0; h < 8; ++h)
+          if (h < n_rep) acc[h][0] += pr[h] * vv.x, acc[h][1] += pr[h] * vv.y;
       }
     }
-    *reinterpret_cast<float4*>(&sm->p[warp][lane][0]) = make_float4(d0[0], d0[1], d0[2], d0[3]);
-    *reinterpret_cast<float4*>(&sm->p[warp][lane][4]) = make_float4(d0[4], d0[5], d0[6], d0[7]);
-    *reinterpret_cast<float4*>(&sm->p[warp][lane + 32][0]) = make_float4(d1[0], d1[1], d1[2], d1[3]);
-    *reinterpret_cast<float4*>(&sm->p[warp][lane + 32][4]) = make_float4(d1[4], d1[5], d1[6], d1[7]);
-    __syncwarp();
-    // P.V: lane = dims (2 lane, 2 lane + 1)
-#pragma unroll 8
-    for (int t = 0; t < 64; ++t) {
-      const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vb + t * 64 + 2 * lane));
-      const float4 pa = *reinterpret_cast<const float4*>(&sm->p[warp][t][0]);
-      const float4 pb = *reinterpret_cast<const float4*>(&sm->p[warp][t][4]);
-      const float pr[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
-#pragma unroll
-      for (int h = 0; h < 8; ++h)
-        if (h < n_rep) acc[h][0] += pr[h] * vv.x, acc[h][1] += pr[h] * vv.y;
-    }
-    __syncwarp();  // the next bulk copy overwrites this warp's K/V buffers
+    // both warps of the pair are done with the buffers before the next copies overwrite them
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
   }
 #pragma unroll
   for (int h = 0; h < 8; ++h) {
@@ -265,7 +277,7 @@ __global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(const Attn
     float L = 0.f, O = 0.f;
 #pragma unroll
     for (int w = 0; w < kAttnWarps; ++w) {
-      const float wgt = exp2f(sm->ml[w][h][0] - M);  // 0 for a warp that walked no page (m = -inf, l = 0)
+      const float wgt = exp2f(sm->ml[w][h][0] - M);  // 0 for a warp that saw no token (m = -inf, l = 0)
       L += wgt * sm->ml[w][h][1];
       O += wgt * sm->o[w][h][d];
     }
@@ -275,15 +287,31 @@ __global__ void __launch_bounds__(32 * kAttnWarps) attn_decode_kernel(const Attn
   }
 }
 
-int launch_attn_decode(const AttnDecParams& p, int B, cudaStream_t stream) {
+int launch_attn_decode(const AttnDecParams& p, int B, int n_layers, cudaStream_t stream) {
   if (p.n_rep < 1 || p.n_rep > 8) return set_error(NT_ERR_INVALID, "attention: %d query heads per KV head unsupported (1..8)", p.n_rep);
   static bool attr_set = false;
-  const int smem = int(sizeof(AttnWarpSmem)) + 128;
+  const int smem = int(sizeof(AttnWarpSmem)) + 1024;
   if (!attr_set) {
     NT_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  return launch_kernel(attn_decode_kernel, dim3(p.kv.n_kv_heads, B), dim3(32 * kAttnWarps), smem, stream, true, p);
+  // one descriptor over the whole paged pool, viewed as rows of 64 bf16 (a K or V page of one head = 64 rows)
+  static std::mutex mu;
+  static CUtensorMap cached;
+  static const void* c_base = nullptr;
+  static long long c_rows = 0;
+  const long long rows = static_cast<long long>(n_layers) * 2 * p.kv.num_pages * p.kv.n_kv_heads * 64;
+  if (rows >= (1ll << 31)) return set_error(NT_ERR_INVALID, "attention: KV pool too large for one TMA descriptor");
+  CUtensorMap kmap;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (c_base != p.kv.pages || c_rows != rows) {
+      if (int rc = make_tmap(&cached, NT_BF16, p.kv.pages, static_cast<uint64_t>(rows), 64, 64, 64)) return rc;
+      c_base = p.kv.pages, c_rows = rows;
+    }
+    kmap = cached;
+  }
+  return launch_kernel(attn_decode_kernel, dim3(p.kv.n_kv_heads, B), dim3(32 * kAttnWarps), smem, stream, true, p, kmap);
 }
 
 // =================================================================================== sampler

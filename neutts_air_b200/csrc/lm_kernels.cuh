@@ -61,7 +61,7 @@ struct AttnDecParams {
   __nv_bfloat16* out_bf16;  // optional copy for the tensor-core o_proj
   int max_splits;
 };
-int launch_attn_decode(const AttnDecParams& p, int B, cudaStream_t stream);
+int launch_attn_decode(const AttnDecParams& p, int B, int n_layers, cudaStream_t stream);  // n_layers: extent of the KV pool
 
 struct SamplerParams {
   const float* logits;  // [B, V]

@@ -103,12 +103,15 @@ def test_lm_ragged_batch_prefill_and_decode(cuda, mega, monkeypatch):
         assert rel_err(got[b], mir) < 6e-3 and max_err(got[b], mir) < 5e-2 * float(mir.std()), (b, rel_err(got[b], mir))
 
 
-@pytest.mark.parametrize("B", [6, 10, 18], ids=["2-megakernel-instances", "3-megakernel-instances", "per-op-tcgen05"])
-def test_lm_batched_decode(cuda, B):
-    """batch 5..16 runs as concurrent megakernel instances of <= 4 sequences on disjoint SM subsets (fp32
-    activations, same arithmetic as batch 1); batch > 16 decodes through the per-op tcgen05 GEMM path with
-    M = batch (bf16 GEMM inputs).  Prefill is the tensor-core path in every case, so the bar is the
-    pure-reference one."""
+@pytest.mark.parametrize("B,mega_max", [(6, None), (18, None), (10, "16")],
+                         ids=["per-op-tcgen05-b6", "per-op-tcgen05-b18", "3-megakernel-instances"])
+def test_lm_batched_decode(cuda, B, mega_max, monkeypatch):
+    """batch > 4 decodes through the per-op chain with tcgen05 GEMMs, M = batch (bf16 GEMM inputs, split-K
+    o/down projections folded by the next RMSNorm).  NT_MEGA_MAX_BATCH=16 instead runs concurrent megakernel
+    instances of <= 4 sequences on disjoint SM subsets (fp32 activations, same arithmetic as batch 1).
+    Prefill is the tensor-core path in every case, so the bar is the pure-reference one."""
+    if mega_max:
+        monkeypatch.setenv("NT_MEGA_MAX_BATCH", mega_max)
     cfg, w, lm = _setup(SMALL, 31, max_batch=20, max_ctx=256)
     g = torch.Generator().manual_seed(2)
     lens = [20, 41, 64, 65, 9, 30, 17, 80, 33, 5, 12, 70, 3, 44, 27, 90, 61, 8][:B]
