@@ -361,7 +361,7 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
       AttnPrefillParams ap;
       ap.q = lm->q, ap.kv = kv, ap.layer = l, ap.n_heads = c.n_heads, ap.n_rep = c.n_heads / c.n_kv_heads;
       ap.scale_log2 = scale_log2, ap.cu_seqlens = lm->cu_dev, ap.out = lm->attn_bf16, ap.max_len = max_len;
-      if ((rc = launch_attn_prefill(ap, B, stream))) return rc;
+      if ((rc = launch_attn_prefill(ap, B, c.n_layers, stream))) return rc;
     } else {
       AttnDecParams ad;
       ad.q = lm->q, ad.kv = kv, ad.layer = l, ad.n_heads = c.n_heads, ad.n_rep = c.n_heads / c.n_kv_heads;

@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include <cfloat>
+#include <cstdlib>
 #include <mutex>
 
 namespace nt {
@@ -37,6 +38,10 @@ static GemvSmemPlan gemv_plan(int K, int nb) {
   p.units_per_stage = (p.wpu == 1) ? kConsumerWarps : 1;
   p.stage_bytes = unit_bytes * p.units_per_stage;
   p.nstages = (p.wpu == 1) ? 3 : 4;
+  if (const char* e = getenv("NT_GEMV_STAGES")) {  // experiments (profiles/probe_head_stages.py)
+    const int n = atoi(e);
+    if (n >= 2 && n <= 8) p.nstages = n;
+  }
   size_t off = 0;
   p.ring_off = off;
   off += size_t(p.stage_bytes) * p.nstages;
@@ -148,6 +153,25 @@ int launch_gemv(const GemvParams& p, int nb, int num_sms, cudaStream_t stream) {
     attr_bytes[nb] = plan.total;
   }
   return launch_kernel(kern, dim3(grid), dim3(kGemvThreads), plan.total, stream, true, p, plan);
+}
+
+// One TMA descriptor over the whole paged KV pool viewed as rows of 64 bf16 (a K or V page of one head = 64 rows,
+// box = 64 rows x 128 bytes, SWIZZLE_128B).  Row of (layer, k|v, page, head, token):
+//   ((layer * 2 + is_v) * num_pages + page) * n_kv_heads + head) * 64 + token
+static int kv_pool_tmap(const KVLayout& kv, int n_layers, CUtensorMap* out) {
+  static std::mutex mu;
+  static CUtensorMap cached;
+  static const void* c_base = nullptr;
+  static long long c_rows = 0;
+  const long long rows = static_cast<long long>(n_layers) * 2 * kv.num_pages * kv.n_kv_heads * 64;
+  if (rows >= (1ll << 31)) return set_error(NT_ERR_INVALID, "attention: KV pool too large for one TMA descriptor");
+  std::lock_guard<std::mutex> lock(mu);
+  if (c_base != kv.pages || c_rows != rows) {
+    if (int rc = make_tmap(&cached, NT_BF16, kv.pages, static_cast<uint64_t>(rows), 64, 64, 64)) return rc;
+    c_base = kv.pages, c_rows = rows;
+  }
+  *out = cached;
+  return NT_OK;
 }
 
 // =================================================================================== decode attention
@@ -295,22 +319,8 @@ int launch_attn_decode(const AttnDecParams& p, int B, int n_layers, cudaStream_t
     NT_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  // one descriptor over the whole paged pool, viewed as rows of 64 bf16 (a K or V page of one head = 64 rows)
-  static std::mutex mu;
-  static CUtensorMap cached;
-  static const void* c_base = nullptr;
-  static long long c_rows = 0;
-  const long long rows = static_cast<long long>(n_layers) * 2 * p.kv.num_pages * p.kv.n_kv_heads * 64;
-  if (rows >= (1ll << 31)) return set_error(NT_ERR_INVALID, "attention: KV pool too large for one TMA descriptor");
   CUtensorMap kmap;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (c_base != p.kv.pages || c_rows != rows) {
-      if (int rc = make_tmap(&cached, NT_BF16, p.kv.pages, static_cast<uint64_t>(rows), 64, 64, 64)) return rc;
-      c_base = p.kv.pages, c_rows = rows;
-    }
-    kmap = cached;
-  }
+  if (int rc = kv_pool_tmap(p.kv, n_layers, &kmap)) return rc;
   return launch_kernel(attn_decode_kernel, dim3(p.kv.n_kv_heads, B), dim3(32 * kAttnWarps), smem, stream, true, p, kmap);
 }
 
@@ -475,98 +485,174 @@ int launch_rope_append(const float* qkv, int T, int qkv_n, const int32_t* tok_se
                        tok_pos, n_heads, inv_freq, q_out, kv, layer);
 }
 
-// Causal GQA attention for prefill, fp32 math on CUDA cores (first version: correctness and a
-// sane baseline; the tensor-core flash kernel replaces it for large batches).
-// grid (ceil(max_len/16), n_kv_heads, B); thread = one (query, head-in-group) row.
+// Causal GQA flash attention for prefill on tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate).
+// grid (ceil(max_len/16), n_kv_heads, B), n_rep warps: a CTA owns 16 query tokens of one sequence and one KV head;
+// warp h holds the 16 x 64 query tile of head kvh*n_rep + h as A fragments (bf16, softmax scale * log2e folded in)
+// and all warps share the K/V tiles.  A KV tile is one 64-token page: K and V land in shared memory through the
+// SWIZZLE_128B pool descriptor (double-buffered, one mbarrier per buffer), B fragments come from ldmatrix
+// (K: plain, V: .trans) with the swizzle applied to the row addresses.  Online softmax in the log2 domain on the
+// accumulator fragments (quad shuffles for row statistics); P is rounded to bf16 for the P.V MMA (as in
+// FlashAttention-2).  Replaces a CUDA-core kernel that took 81 % of the prefill (451 us per layer at batch 1).
+NT_DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+NT_DEVINL void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+NT_DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
 constexpr int kPfQ = 16;
-__global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnPrefillParams p) {
-  __shared__ __align__(16) __nv_bfloat16 sK[32 * 64];
-  __shared__ __align__(16) __nv_bfloat16 sV[32 * 64];
+__global__ void __launch_bounds__(256) attn_prefill_kernel(const AttnPrefillParams p, const __grid_constant__ CUtensorMap kvmap) {
+  __shared__ __align__(1024) __nv_bfloat16 sK[2][64 * 64];
+  __shared__ __align__(1024) __nv_bfloat16 sV[2][64 * 64];
+  __shared__ __align__(8) uint64_t full_bar[2];
   pdl_launch_dependents();
+  const int qb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    tma_prefetch_desc(&kvmap);
+    mbar_init(&full_bar[0], 1);
+    mbar_init(&full_bar[1], 1);
+    fence_barrier_init();
+  }
   pdl_wait();
-  const int qb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
-  const int t0 = p.cu_seqlens[b], len = p.cu_seqlens[b + 1] - t0;
-  if (qb * kPfQ >= len) return;
-  const int n_rep = p.n_rep;
-  const int qi = tid / n_rep, h = tid - qi * n_rep;
-  const int tq = qb * kPfQ + qi;
-  const bool active = (qi < kPfQ) && (tq < len);
-  float q[64], o[64];
-  float m = -INFINITY, l = 0.f;
-  if (active) {
-    const float4* qp = reinterpret_cast<const float4*>(p.q + (static_cast<long long>(t0 + tq) * p.n_heads + kvh * n_rep + h) * 64);
+  const int t0 = __ldg(p.cu_seqlens + b), len = __ldg(p.cu_seqlens + b + 1) - t0;
+  const int q0 = qb * kPfQ;
+  if (q0 >= len) return;  // CTA-uniform
+  __syncthreads();
+  const int kend = min(len, q0 + kPfQ);      // keys [0, kend) are visible to some query of this block
+  const int ntiles = (kend + 63) >> 6;
+  const int krow0 = p.layer * 2 * p.kv.num_pages * p.kv.n_kv_heads * 64;
+  const int vrow0 = krow0 + p.kv.num_pages * p.kv.n_kv_heads * 64;
+  auto issue = [&](int tile) {
+    const int page = __ldg(p.kv.page_table + b * p.kv.max_pages_per_seq + tile);
+    const int buf = tile & 1;
+    asm volatile("fence.proxy.async;" ::: "memory");
+    mbar_arrive_expect_tx(&full_bar[buf], 2 * 8192);
+    tma_load_2d(sK[buf], &kvmap, 0, krow0 + (page * p.kv.n_kv_heads + kvh) * 64, &full_bar[buf]);
+    tma_load_2d(sV[buf], &kvmap, 0, vrow0 + (page * p.kv.n_kv_heads + kvh) * 64, &full_bar[buf]);
+  };
+  if (tid == 0) issue(0);
+
+  // query fragments of head `warp`: rows g and g + 8 of the block, 4 k-steps of 16 dims
+  const int g = lane >> 2, t = lane & 3;
+  const int head = kvh * p.n_rep + warp;
+  const int r0 = min(q0 + g, len - 1), r1 = min(q0 + g + 8, len - 1);  // clamp the ragged tail (stores are masked)
+  uint32_t qa[4][4];
+  {
+    const float* q0p = p.q + (static_cast<long long>(t0 + r0) * p.n_heads + head) * 64;
+    const float* q1p = p.q + (static_cast<long long>(t0 + r1) * p.n_heads + head) * 64;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float4 v = qp[j];
-      q[4 * j] = v.x * p.scale_log2, q[4 * j + 1] = v.y * p.scale_log2, q[4 * j + 2] = v.z * p.scale_log2,
-            q[4 * j + 3] = v.w * p.scale_log2;
+    for (int j = 0; j < 4; ++j) {
+      const float2 a0 = *reinterpret_cast<const float2*>(q0p + 16 * j + 2 * t);
+      const float2 a1 = *reinterpret_cast<const float2*>(q1p + 16 * j + 2 * t);
+      const float2 a2 = *reinterpret_cast<const float2*>(q0p + 16 * j + 8 + 2 * t);
+      const float2 a3 = *reinterpret_cast<const float2*>(q1p + 16 * j + 8 + 2 * t);
+      qa[j][0] = pack_bf16x2(a0.x * p.scale_log2, a0.y * p.scale_log2);
+      qa[j][1] = pack_bf16x2(a1.x * p.scale_log2, a1.y * p.scale_log2);
+      qa[j][2] = pack_bf16x2(a2.x * p.scale_log2, a2.y * p.scale_log2);
+      qa[j][3] = pack_bf16x2(a3.x * p.scale_log2, a3.y * p.scale_log2);
     }
   }
+  float o[8][4];
 #pragma unroll
-  for (int j = 0; j < 64; ++j) o[j] = 0.f;
-  const int kend = min(len, (qb + 1) * kPfQ);
-  const int ntiles = (kend + 31) >> 5;
+  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // rows g / g + 8 (l: this lane's partial sum)
+  const int qi0 = q0 + g, qi1 = q0 + g + 8;
+  // ldmatrix row address pieces: lane supplies row (lane & 7) of matrix (lane >> 3)
+  const int lrow = lane & 7, lmat = lane >> 3;
+
   for (int tile = 0; tile < ntiles; ++tile) {
-    const int k0 = tile * 32;
-    const int page = p.kv.page_table[b * p.kv.max_pages_per_seq + (k0 >> 6)];
-    const uint4* gk = reinterpret_cast<const uint4*>(p.kv.page_ptr(p.layer, 0, page, kvh) + (k0 & 63) * 64);
-    const uint4* gv = reinterpret_cast<const uint4*>(p.kv.page_ptr(p.layer, 1, page, kvh) + (k0 & 63) * 64);
-    __syncthreads();
-    for (int i = tid; i < 256; i += 128) {
-      reinterpret_cast<uint4*>(sK)[i] = gk[i];
-      reinterpret_cast<uint4*>(sV)[i] = gv[i];
-    }
-    __syncthreads();
-    if (!active) continue;
-    float s[32];
-    float tmax = -INFINITY;
+    const int buf = tile & 1;
+    __syncthreads();  // every warp is done with the buffer the next copy overwrites
+    if (tid == 0 && tile + 1 < ntiles) issue(tile + 1);
+    mbar_wait(&full_bar[buf], (tile >> 1) & 1);
+    const uint32_t kbase = smem_u32(sK[buf]), vbase = smem_u32(sV[buf]);
+
+    // S = Q K^T : 8 key groups of 8 tokens
+    float sc[8][4];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float d = 0.f;
-      const uint4* kr = reinterpret_cast<const uint4*>(sK + j * 64);
+    for (int n = 0; n < 8; ++n) {
+      sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+      const int row = 8 * n + lrow;  // key token within the tile; row & 7 == lrow
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float f[8];
-        bf16x8_to_f32(kr[c], f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) d += q[8 * c + e] * f[e];
-      }
-      s[j] = (k0 + j <= tq) ? d : -INFINITY;  // causal mask (key position <= query position)
-      tmax = fmaxf(tmax, s[j]);
-    }
-    const float mn = fmaxf(m, tmax);  // key 0 is always visible -> finite from the first tile on
-    const float corr = exp2f(m - mn);
-    l *= corr;
-#pragma unroll
-    for (int j = 0; j < 64; ++j) o[j] *= corr;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float pj = exp2f(s[j] - mn);
-      l += pj;
-      const uint4* vr = reinterpret_cast<const uint4*>(sV + j * 64);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float f[8];
-        bf16x8_to_f32(vr[c], f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[8 * c + e] += pj * f[e];
+      for (int half = 0; half < 2; ++half) {  // dims 0..31 / 32..63: 4 chunks of 8 dims each
+        uint32_t kb[4];
+        ldmatrix_x4(kb, kbase + row * 128 + (((4 * half + lmat) ^ lrow) << 4));
+        mma_bf16_16816(sc[n], qa[2 * half], kb[0], kb[1]);
+        mma_bf16_16816(sc[n], qa[2 * half + 1], kb[2], kb[3]);
       }
     }
-    m = mn;
+    // causal / length mask (only tiles that reach past the first query of the block need it)
+    const int k0 = tile * 64;
+    if (k0 + 63 > q0 || k0 + 64 > len) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const int kv0 = k0 + 8 * n + 2 * t;
+        if (kv0 > qi0 || kv0 >= len) sc[n][0] = -INFINITY;
+        if (kv0 + 1 > qi0 || kv0 + 1 >= len) sc[n][1] = -INFINITY;
+        if (kv0 > qi1 || kv0 >= len) sc[n][2] = -INFINITY;
+        if (kv0 + 1 > qi1 || kv0 + 1 >= len) sc[n][3] = -INFINITY;
+      }
+    }
+    // online softmax (base 2)
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) mx0 = fmaxf(mx0, fmaxf(sc[n][0], sc[n][1])), mx1 = fmaxf(mx1, fmaxf(sc[n][2], sc[n][3]));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)), mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)), mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // key 0 is visible to every query: finite from tile 0 on
+    const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+    m0 = mn0, m1 = mn1;
+    l0 *= c0, l1 *= c1;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) o[n][0] *= c0, o[n][1] *= c0, o[n][2] *= c1, o[n][3] *= c1;
+    uint32_t pa[4][4];  // P as A fragments: k-step j covers key groups 2j, 2j+1
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float p00 = exp2f(sc[n][0] - mn0), p01 = exp2f(sc[n][1] - mn0);
+      const float p10 = exp2f(sc[n][2] - mn1), p11 = exp2f(sc[n][3] - mn1);
+      l0 += p00 + p01, l1 += p10 + p11;
+      pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p00, p01);
+      pa[n >> 1][(n & 1) * 2 + 1] = pack_bf16x2(p10, p11);
+    }
+    // O += P V : k-steps of 16 keys, output dim groups of 8 (two per ldmatrix)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = 16 * j + 8 * (lmat & 1) + lrow;  // key token; row & 7 == lrow
+#pragma unroll
+      for (int nd = 0; nd < 8; nd += 2) {
+        uint32_t vb[4];
+        ldmatrix_x4_trans(vb, vbase + row * 128 + (((nd + (lmat >> 1)) ^ lrow) << 4));
+        mma_bf16_16816(o[nd], pa[j], vb[0], vb[1]);
+        mma_bf16_16816(o[nd + 1], pa[j], vb[2], vb[3]);
+      }
+    }
   }
-  if (active) {
-    const float inv = 1.0f / l;
-    __nv_bfloat16* op = p.out + (static_cast<long long>(t0 + tq) * p.n_heads + kvh * n_rep + h) * 64;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1), l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1), l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  __nv_bfloat16* o0p = p.out + (static_cast<long long>(t0 + qi0) * p.n_heads + head) * 64 + 2 * t;
+  __nv_bfloat16* o1p = p.out + (static_cast<long long>(t0 + qi1) * p.n_heads + head) * 64 + 2 * t;
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      reinterpret_cast<uint4*>(op)[j] =
-          make_uint4(pack_bf16x2(o[8 * j] * inv, o[8 * j + 1] * inv), pack_bf16x2(o[8 * j + 2] * inv, o[8 * j + 3] * inv),
-                     pack_bf16x2(o[8 * j + 4] * inv, o[8 * j + 5] * inv), pack_bf16x2(o[8 * j + 6] * inv, o[8 * j + 7] * inv));
+  for (int n = 0; n < 8; ++n) {
+    if (qi0 < len) *reinterpret_cast<uint32_t*>(o0p + 8 * n) = pack_bf16x2(o[n][0] * i0, o[n][1] * i0);
+    if (qi1 < len) *reinterpret_cast<uint32_t*>(o1p + 8 * n) = pack_bf16x2(o[n][2] * i1, o[n][3] * i1);
   }
 }
-int launch_attn_prefill(const AttnPrefillParams& p, int B, cudaStream_t s) {
-  if (p.n_rep * kPfQ > 128) return set_error(NT_ERR_INVALID, "prefill attention: %d query heads per KV head unsupported", p.n_rep);
-  return launch_kernel(attn_prefill_kernel, dim3((p.max_len + kPfQ - 1) / kPfQ, p.kv.n_kv_heads, B), dim3(128), 0, s, true, p);
+int launch_attn_prefill(const AttnPrefillParams& p, int B, int n_layers, cudaStream_t s) {
+  if (p.n_rep < 1 || p.n_rep > 8) return set_error(NT_ERR_INVALID, "prefill attention: %d query heads per KV head unsupported", p.n_rep);
+  CUtensorMap kvmap;
+  if (int rc = kv_pool_tmap(p.kv, n_layers, &kvmap)) return rc;
+  return launch_kernel(attn_prefill_kernel, dim3((p.max_len + kPfQ - 1) / kPfQ, p.kv.n_kv_heads, B), dim3(32 * p.n_rep), 0, s, true, p,
+                       kvmap);
 }
 
 __global__ void gather_rows_kernel(const float* src, const int32_t* rows, int cols, float* dst) {

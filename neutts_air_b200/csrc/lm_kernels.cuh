@@ -113,7 +113,7 @@ struct AttnPrefillParams {
   __nv_bfloat16* out;         // [T, n_heads*64]
   int max_len;
 };
-int launch_attn_prefill(const AttnPrefillParams& p, int B, cudaStream_t s);
+int launch_attn_prefill(const AttnPrefillParams& p, int B, int n_layers, cudaStream_t s);
 int launch_gather_rows(const float* src, const int32_t* rows, int n, int cols, float* dst, cudaStream_t s);
 
 }  // namespace nt

@@ -108,20 +108,35 @@ def apply_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.T
     return x * cos[..., None, :] + rot * sin[..., None, :]
 
 
-def attention(q, k, v, causal_offset: int | None, n_rep: int):
+def attention(q, k, v, causal_offset: int | None, n_rep: int, mma_bf16: bool = False):
     """modeling_qwen2.py:149-183 (eager path of record): repeat_kv, QK^T * d^-1/2,
     additive causal mask, fp32 softmax, PV.
     q: [Tq, Hq, d], k/v: [Tk, Hkv, d].  causal_offset = absolute position of q[0]
-    minus position of k[0] (None = bidirectional)."""
+    minus position of k[0] (None = bidirectional).
+
+    mma_bf16 (mirror of the CUDA tensor-core prefill kernel, not reference semantics): the query is
+    scaled by d^-1/2 * log2(e) and rounded to bf16, the probabilities 2^(s - max) are rounded to bf16
+    before P.V, the normaliser sums the unrounded probabilities."""
     Tq, Hq, d = q.shape
     Tk = k.shape[0]
     k = k.repeat_interleave(n_rep, dim=1)
     v = v.repeat_interleave(n_rep, dim=1)
-    s = torch.einsum("qhd,khd->hqk", q, k) * (d ** -0.5)
+    mask = None
     if causal_offset is not None:
         qi = torch.arange(Tq)[:, None] + causal_offset
         kj = torch.arange(Tk)[None, :]
-        s = s.masked_fill(kj > qi, float("-inf"))
+        mask = kj > qi
+    if mma_bf16:
+        qs = (q * (d ** -0.5 * 1.4426950408889634)).bfloat16().float()
+        s = torch.einsum("qhd,khd->hqk", qs, k)
+        if mask is not None:
+            s = s.masked_fill(mask, float("-inf"))
+        pr = torch.exp2(s - s.max(dim=-1, keepdim=True).values)
+        o = torch.einsum("hqk,khd->qhd", pr.bfloat16().float(), v)
+        return o / pr.sum(dim=-1).T[:, :, None]
+    s = torch.einsum("qhd,khd->hqk", q, k) * (d ** -0.5)
+    if mask is not None:
+        s = s.masked_fill(mask, float("-inf"))
     p = torch.softmax(s.float(), dim=-1).to(q.dtype)
     return torch.einsum("hqk,khd->qhd", p, v)
 
@@ -157,7 +172,8 @@ def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | Non
     not part of the reference semantics; ``mirror=None`` is the reference):
       "decode"  (GEMV path, batch <= 4): K/V rounded to bf16 when cached, all else fp32;
       "prefill" (tensor-core path): additionally the normalised activations, the
-                attention output and the SwiGLU output are rounded to bf16 (GEMM A operands);
+                attention output and the SwiGLU output are rounded to bf16 (GEMM A operands), and
+                attention runs on bf16 tensor-core operands (scaled query and probabilities);
       "batched" (tensor-core decode, batch > 4): as "prefill" plus a bf16 lm_head input.
 
     Returns (logits [T, V], hiddens list or None).
@@ -185,7 +201,7 @@ def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | Non
         if kv_round_bf16:
             k, v = k.bfloat16().float(), v.bfloat16().float()
         kk, vv = cache.update(li, k, v)                            # :225
-        a = attention(q, kk, vv, causal_offset=past, n_rep=n_rep)  # :231
+        a = attention(q, kk, vv, causal_offset=past, n_rep=n_rep, mma_bf16=(mirror == "prefill"))  # :231
         a = rb(a.reshape(T, -1))
         h = h + a @ L["wo"].T                                      # :244, :302
         h_mid = h
