@@ -201,7 +201,7 @@ def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | Non
         if kv_round_bf16:
             k, v = k.bfloat16().float(), v.bfloat16().float()
         kk, vv = cache.update(li, k, v)                            # :225
-        a = attention(q, kk, vv, causal_offset=past, n_rep=n_rep, mma_bf16=(mirror == "prefill"))  # :231
+        a = attention(q, kk, vv, causal_offset=past, n_rep=n_rep, mma_bf16=(mirror in ("prefill", "batched")))  # :231
         a = rb(a.reshape(T, -1))
         h = h + a @ L["wo"].T                                      # :244, :302
         h_mid = h
