@@ -38,6 +38,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1, help="utterances per GPU per step (metric is quoted at 1, 8, 64)")
+    ap.add_argument("--workload", default="fixed", choices=["fixed", "mixed"],
+                    help="fixed: every prompt 500 tokens (configs[1]); mixed: prompt lengths U{200..1400}, seeded (configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the batch 8 / 64 lines reported under 'batches' (N=1 runs only)")
     return ap.parse_args()
@@ -54,13 +56,16 @@ def peaks():
 # ----------------------------------------------------------------------------------------------
 # synthetic model + workload (identical on every rank and for both arms)
 # ----------------------------------------------------------------------------------------------
-def synth_prompts(n, vocab, speech_base, seed):
-    """128 uniform text ids + 372 speech ids (dave.pt-shaped reference), P = 500."""
+def synth_prompts(n, vocab, speech_base, seed, mixed=False):
+    """128 uniform text ids + 372 speech ids (dave.pt-shaped reference), P = 500.
+    mixed (configs[2]): P_i ~ U{200..1400}, a quarter of it text ids, the rest reference speech ids."""
     g = torch.Generator().manual_seed(seed)
     out = []
     for _ in range(n):
-        text = torch.randint(0, 151643, (PREFILL - 372,), generator=g)
-        ref = speech_base + torch.randint(0, 65536, (372,), generator=g)
+        P = int(torch.randint(200, 1401, (1,), generator=g)) if mixed else PREFILL
+        n_text = P // 4 if mixed else PREFILL - 372
+        text = torch.randint(0, 151643, (n_text,), generator=g)
+        ref = speech_base + torch.randint(0, 65536, (P - n_text,), generator=g)
         out.append(torch.cat((text, ref)).tolist())
     return out
 
@@ -204,7 +209,7 @@ def main_reference(args):
 _WEIGHTS = {}
 
 
-def build_engines(device, batch):
+def build_engines(device, batch, prefill_tokens=None):
     from neutts_air_b200 import synthetic
     from neutts_air_b200.codec import CodecDecoder, CodecShape
     from neutts_air_b200.lm import LMShape, SpeechLM
@@ -214,7 +219,7 @@ def build_engines(device, batch):
         _WEIGHTS["lm"] = synthetic.lm_state_dict(shape, 0)
         _WEIGHTS["codec"] = synthetic.codec_weights(CodecShape(), 0)
     lm = SpeechLM(shape, _WEIGHTS["lm"], device=device, max_batch=batch, max_ctx=2048, max_new=256,
-                  max_prefill_tokens=batch * PREFILL)
+                  max_prefill_tokens=prefill_tokens or batch * PREFILL)
     codec = CodecDecoder(CodecShape(), _WEIGHTS["codec"], device=device, max_batch=batch, max_frames=256)
     return lm, codec
 
@@ -272,9 +277,10 @@ def main_b200(args):
         td.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     B = args.batch
-    lm, codec = build_engines(dev, B)
     speech_base, eos = 151936, 151670
-    prompts = synth_prompts(B, lm.shape.vocab_size, speech_base, 1234 + rank)
+    mixed = args.workload == "mixed"
+    prompts = synth_prompts(B, 217472, speech_base, 1234 + rank, mixed)
+    lm, codec = build_engines(dev, B, sum(len(p) for p in prompts))
     pinned_ids = torch.tensor([t for p in prompts for t in p], dtype=torch.int32).pin_memory()
     lens = [len(p) for p in prompts]
     h2d_bytes = pinned_ids.numel() * 4
@@ -395,14 +401,16 @@ def main_b200(args):
     cfgs = lm.shape
     p_blk = cfgs.num_layers * ((cfgs.num_heads + 2 * cfgs.num_kv_heads) * 64 * (cfgs.hidden_size + 1) + cfgs.hidden_size * cfgs.num_heads * 64
                                + 3 * cfgs.hidden_size * cfgs.intermediate_size + 2 * cfgs.hidden_size) + cfgs.hidden_size
-    step_bytes = 2 * (p_blk + cfgs.vocab_size * cfgs.hidden_size) + B * (12288 * (PREFILL + DECODE / 2 + 1) + 2 * cfgs.hidden_size)
+    step_bytes = 2 * (p_blk + cfgs.vocab_size * cfgs.hidden_size) + B * (12288 * (sum(lens) / len(lens) + DECODE / 2 + 1) + 2 * cfgs.hidden_size)
     peak, how = peaks()
     line = {
         "metric": "audio-sec/sec (RTF), NeuTTS-Air 500 prefill / 250 decode + NeuCodec decode",
         "value": total_audio / t_dev, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 weights+KV / f32 accumulate (LM), tf32 tensor cores (codec)", "data": "synthetic",
-        "config": {"workload": f"configs[1]: 500 prefill / 250 decode tokens + NeuCodec decode to 24 kHz, batch={B} per GPU",
+        "config": {"workload": (f"configs[2]: mixed-length prompts U{{200..1400}} (mean {sum(lens) / len(lens):.0f}) / 250 decode tokens + NeuCodec "
+                                f"decode to 24 kHz, batch={B} per GPU" if mixed else
+                                f"configs[1]: 500 prefill / 250 decode tokens + NeuCodec decode to 24 kHz, batch={B} per GPU"),
                    "per_gpu_batch": B, "global_batch": B * world, "sharding": "utterances one-per-GPU-slot, weights replicated, "
                    "one all-gather of waveforms" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: 1.1 GB of weights stream per decode step (L2 = 126 MB)", "weights": "seeded random, inferred Air/NeuCodec shapes"},
