@@ -377,7 +377,8 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, boo
   if (split) {
     split->used = 1;
     const int tiles = mt * ((a.N + bn - 1) / bn);
-    if (tiles <= 48 && taps == 1 && a.act == NT_ACT_NONE && !a.out_bf16 && a.out_f32 && a.residual == a.out_f32 && a.ldr == a.ldc &&
+    const bool in_place = a.residual == a.out_f32 && a.ldr == a.ldc;
+    if (tiles <= 48 && taps == 1 && a.act == NT_ACT_NONE && !a.out_bf16 && a.out_f32 && (in_place || !a.residual) &&
         a.valid_period == 0 && num_kb >= 8) {
       int sk = 144 / tiles;
       if (sk > num_kb / 4) sk = num_kb / 4;
@@ -392,7 +393,9 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, boo
   }
 
   const int ctas = mt * ((a.N + bn - 1) / bn) * (ep.split_k > 1 ? ep.split_k : 1);
-  const bool shallow = ctas > num_sms() && ctas <= 2 * num_sms();
+  // two CTAs per SM: grids between one and two waves, and single-row-tile weight streams of many waves (lm_head at
+  // batched decode: 1699 tiles), where one CTA's prologue / epilogue overlaps the other's main loop
+  const bool shallow = ctas > num_sms() && (ctas <= 2 * num_sms() || mt == 1);
 #define NT_GEMM_CASE(FMT, BNV)                                                                           \
   return shallow ? launch_gemm<FMT, BNV, true>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)         \
                  : launch_gemm<FMT, BNV, false>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)

@@ -48,9 +48,10 @@ int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, 
   return NT_OK;
 }
 
-// Optional split-K lease: when the GEMM accumulates in place (residual == out_f32) and has too few tiles to fill
-// the GPU, it writes `used` raw partial slices [used][M][ldc] into ws instead of touching out_f32; the caller
-// must fold them (x += slice 0 + slice 1 + ..., in that order) before x is read -- rmsnorm_rows does.
+// Optional split-K lease: when the GEMM accumulates in place (residual == out_f32) or has no residual, and has too
+// few tiles to fill the GPU, it writes `used` raw partial slices [used][M][ldc] into ws instead of touching out_f32
+// (bias rides on slice 0); the consumer must fold them in slice order (x += s0 + s1 + ... / y = s0 + s1 + ...)
+// -- rmsnorm_rows and rope_append do.
 struct SplitK {
   float* ws;
   size_t ws_floats;

@@ -130,8 +130,8 @@ static size_t lm_carve(const nt_lm_config& c, void* ws, size_t bytes, F&& assign
     (L)->phase_tab = a.take<MegaPhase>(size_t(4) * c.n_layers + 1);                            \
     (L)->ptr_tab = a.take<const float*>(size_t(3) * c.n_layers);                               \
     (L)->gbar = a.take<unsigned>(256);                                                         \
-    (L)->splitk_floats = size_t(8) * 128 * H;                                                  \
-    (L)->splitk_ws = a.take<float>(size_t(8) * 128 * H);                                       \
+    (L)->splitk_floats = size_t(8) * 128 * (qkv_n > H ? qkv_n : H);                            \
+    (L)->splitk_ws = a.take<float>(size_t(8) * 128 * (qkv_n > H ? qkv_n : H));                 \
   }
 
 static int lm_check_config(const nt_lm_config* c) {
@@ -353,10 +353,15 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
     memset(&a, 0, sizeof(a));
     a.dtype = NT_BF16, a.M = rows, a.N = QN, a.K = H, a.A = lm->xn, a.lda = H, a.W = lm->wqkv[l], a.ldw = H;
     a.bias = lm->bqkv[l], a.out_f32 = lm->qkv, a.ldc = QN;
-    if ((rc = gemm_dispatch(a, stream, nullptr, true))) return rc;
+    // few row tiles: the projection splits K into slices that rope_append sums (the bias rides on slice 0)
+    SplitK qsplit;
+    qsplit.ws = lm->splitk_ws, qsplit.ws_floats = lm->splitk_floats, qsplit.used = 1, qsplit.slice_stride = 0;
+    if ((rc = gemm_dispatch(a, stream, allow_split ? &qsplit : nullptr, true))) return rc;
     const int32_t* tseq = mode == 0 ? lm->tok_seq : lm->iota;
     const int32_t* tpos = mode == 0 ? lm->tok_pos : st->seq_lens;
-    if ((rc = launch_rope_append(lm->qkv, rows, QN, tseq, tpos, c.n_heads, lm->inv_freq, lm->q, kv, l, stream))) return rc;
+    if ((rc = launch_rope_append(qsplit.used > 1 ? qsplit.ws : lm->qkv, rows, QN, tseq, tpos, c.n_heads, lm->inv_freq, lm->q, kv, l, stream,
+                                 qsplit.used, qsplit.slice_stride)))
+      return rc;
     if (mode == 0) {
       AttnPrefillParams ap;
       ap.q = lm->q, ap.kv = kv, ap.layer = l, ap.n_heads = c.n_heads, ap.n_rep = c.n_heads / c.n_kv_heads;

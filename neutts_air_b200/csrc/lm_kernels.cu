@@ -617,13 +617,18 @@ int launch_rmsnorm_rows(const float* x, const float* w, float eps, int rows, int
 // thread = one unit (pair of packed columns) of one token
 __global__ void __launch_bounds__(256) rope_append_kernel(const float* qkv, int qkv_n, const int32_t* tok_seq,
                                                           const int32_t* tok_pos, int n_heads, const float* inv_freq,
-                                                          float* q_out, const KVLayout kv, int layer) {
+                                                          float* q_out, const KVLayout kv, int layer, int nparts,
+                                                          long long pstride) {
   pdl_launch_dependents();
   pdl_wait();
   const int t = blockIdx.x;
   const int u = blockIdx.y * 256 + threadIdx.x;
   if (u >= (qkv_n >> 1)) return;
-  const float2 v = *reinterpret_cast<const float2*>(qkv + static_cast<long long>(t) * qkv_n + 2 * u);
+  float2 v = *reinterpret_cast<const float2*>(qkv + static_cast<long long>(t) * qkv_n + 2 * u);
+  for (int z = 1; z < nparts; ++z) {  // split-K slices of the projection, summed in slice order (qkv = slice 0)
+    const float2 w = __ldcg(reinterpret_cast<const float2*>(qkv + z * pstride + static_cast<long long>(t) * qkv_n + 2 * u));
+    v.x += w.x, v.y += w.y;
+  }
   const int head = u >> 5, i = u & 31;
   const int b = tok_seq[t], pos = tok_pos[t];
   const int n_kv = kv.n_kv_heads;
@@ -646,9 +651,10 @@ __global__ void __launch_bounds__(256) rope_append_kernel(const float* qkv, int 
   }
 }
 int launch_rope_append(const float* qkv, int T, int qkv_n, const int32_t* tok_seq, const int32_t* tok_pos, int n_heads,
-                       const float* inv_freq, float* q_out, const KVLayout& kv, int layer, cudaStream_t s) {
+                       const float* inv_freq, float* q_out, const KVLayout& kv, int layer, cudaStream_t s, int nparts,
+                       long long pstride) {
   return launch_kernel(rope_append_kernel, dim3(T, ((qkv_n >> 1) + 255) / 256), dim3(256), 0, s, true, qkv, qkv_n, tok_seq,
-                       tok_pos, n_heads, inv_freq, q_out, kv, layer);
+                       tok_pos, n_heads, inv_freq, q_out, kv, layer, nparts, pstride);
 }
 
 // Causal GQA flash attention for prefill on tensor cores (mma.sync m16n8k16 bf16, fp32 accumulate).

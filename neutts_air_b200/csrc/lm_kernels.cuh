@@ -103,7 +103,8 @@ int launch_rmsnorm_rows(const float* x, const float* w, float eps, int rows, int
                         long long pstride = 0);
 // qkv: [T, qkv_n] fp32 in packed (pair-interleaved) column order -> q natural order + K/V pages
 int launch_rope_append(const float* qkv, int T, int qkv_n, const int32_t* tok_seq, const int32_t* tok_pos, int n_heads,
-                       const float* inv_freq, float* q_out, const KVLayout& kv, int layer, cudaStream_t s);
+                       const float* inv_freq, float* q_out, const KVLayout& kv, int layer, cudaStream_t s, int nparts = 1,
+                       long long pstride = 0);  // nparts > 1: qkv points at split-K slices [nparts][T][qkv_n] to be summed
 struct AttnPrefillParams {
   const float* q;  // [T, n_heads*64]
   KVLayout kv;
