@@ -29,6 +29,12 @@ static bool env_flag(const char* name) {
   const char* v = getenv(name);
   return v && v[0] && v[0] != '0';
 }
+// largest batch the per-op GEMV chain takes when the megakernel is off (above it: tcgen05 GEMM chain with M = batch)
+static int gemv_max_batch() {
+  const char* e = getenv("NT_GEMV_MAX_BATCH");
+  const int n = e ? atoi(e) : 4;
+  return n < 0 ? 0 : (n > 4 ? 4 : n);
+}
 // largest batch the persistent decode megakernel takes (default 4; up to 16 via concurrent instances)
 static int mega_max_batch() {
   const char* e = getenv("NT_MEGA_MAX_BATCH");
@@ -304,7 +310,7 @@ static int check_sampling(const nt_lm* lm, const nt_lm_state* st, const nt_sampl
 // lm_head on B hidden rows (fp32, un-normalised) -> lm->logits / `logits`
 static int lm_head_rows(nt_lm* lm, const float* hrows, int B, float* logits, cudaStream_t stream, const SplitK* pend = nullptr) {
   const nt_lm_config& c = lm->cfg;
-  if (B <= 4) {
+  if (B <= gemv_max_batch()) {
     GemvParams g;
     memset(&g, 0, sizeof(g));
     g.W = lm->lm_head, g.rows = c.vocab_size, g.K = c.hidden;
@@ -315,7 +321,7 @@ static int lm_head_rows(nt_lm* lm, const float* hrows, int B, float* logits, cud
   }
   // pend: the last down_proj left split-K slices that still have to be folded into hrows (batched decode only)
   const bool fold = pend && pend->used > 1;
-  if (fold && B <= 4) return set_error(NT_ERR_STATE, "lm_head: pending split-K slices on the GEMV path");
+  if (fold && B <= gemv_max_batch()) return set_error(NT_ERR_STATE, "lm_head: pending split-K slices on the GEMV path");
   int rc = launch_rmsnorm_rows(hrows, lm->final_norm, c.rms_eps, B, c.hidden, nullptr, lm->xn, stream, fold ? pend->ws : nullptr,
                                fold ? pend->used : 0, fold ? pend->slice_stride : 0);
   if (rc) return rc;
@@ -440,7 +446,7 @@ static int decode_step(nt_lm* lm, const nt_lm_state* st, int B, const nt_samplin
   int rc;
   SplitK tail;
   tail.ws = nullptr, tail.ws_floats = 0, tail.used = 1, tail.slice_stride = 0;
-  if (B <= 4) {
+  if (B <= gemv_max_batch()) {
     const KVLayout kv = make_kv(lm, st);
     const int H = c.hidden, I = c.inter, HD = c.n_heads * 64;
     const float scale_log2 = (1.0f / 8.0f) * 1.4426950408889634f;
