@@ -101,6 +101,36 @@ NT_DEVINL void unit_dot(const uint4* r0, const uint4* r1, const float4* xs, int 
   }
 }
 
+// Batch-1 fast path for K <= 1024: the lane's slice of the input vector (chunks lane, lane+32, lane+64, lane+96)
+// stays in registers for the whole phase, so a unit costs two 16-byte shared loads per chunk instead of four, and
+// the fully unrolled loop puts all weight loads of the unit in flight at once.
+struct XRegs {
+  float4 a[4], b[4];
+};
+NT_DEVINL void load_xregs(const float4* xs, int nch, int lane, XRegs& xr) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane + 32 * k;
+    const bool ok = c < nch;
+    xr.a[k] = ok ? xs[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    xr.b[k] = ok ? xs[nch + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+NT_DEVINL void unit_dot_x1(const uint4* r0, const uint4* r1, int nch, int lane, const XRegs& xr, float& d0, float& d1) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane + 32 * k;
+    if (c < nch) {
+      float f0[8], f1[8];
+      bf16x8_to_f32(r0[c], f0);
+      bf16x8_to_f32(r1[c], f1);
+      const float4 xa = xr.a[k], xb = xr.b[k];
+      d0 += f0[0] * xa.x + f0[1] * xa.y + f0[2] * xa.z + f0[3] * xa.w + f0[4] * xb.x + f0[5] * xb.y + f0[6] * xb.z + f0[7] * xb.w;
+      d1 += f1[0] * xa.x + f1[1] * xa.y + f1[2] * xa.z + f1[3] * xa.w + f1[4] * xb.x + f1[5] * xb.y + f1[6] * xb.z + f1[7] * xb.w;
+    }
+  }
+}
+
 // Epilogue of one unit (rows 2u, 2u+1).  All lanes hold the full sums; lane b finishes batch row b.
 template <int NB>
 NT_DEVINL void gemv_epilogue(const GemvParams& p, int u, float (&d0)[NB], float (&d1)[NB], int lane) {
@@ -167,7 +197,8 @@ NT_DEVINL void gemv_epilogue(const GemvParams& p, int u, float (&d0)[NB], float 
 // `release` is called once per warp as soon as the warp has finished reading the stage.
 template <int NB, typename Release>
 NT_DEVINL void gemv_consume_stage(const GemvParams& p, const uint8_t* st, const float4* xs, float* red, int wpu,
-                                  int first_unit_local, int units_in_stage, int u_begin, int parity, Release release) {
+                                  int first_unit_local, int units_in_stage, int u_begin, int parity, Release release,
+                                  const XRegs& xr, bool use_xr) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nch = p.K >> 3;
   const int unit_bytes = 4 * p.K;
@@ -178,7 +209,10 @@ NT_DEVINL void gemv_consume_stage(const GemvParams& p, const uint8_t* st, const 
     const bool has = warp < units_in_stage;
     if (has) {
       const uint4* r0 = reinterpret_cast<const uint4*>(st + static_cast<size_t>(warp) * unit_bytes);
-      unit_dot<NB>(r0, r0 + nch, xs, nch, 0, nch, lane, d0, d1);
+      if (NB == 1 && use_xr)
+        unit_dot_x1(r0, r0 + nch, nch, lane, xr, d0[0], d1[0]);
+      else
+        unit_dot<NB>(r0, r0 + nch, xs, nch, 0, nch, lane, d0, d1);
     }
     __syncwarp();
     release();

@@ -121,15 +121,20 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
 
   // ---- consumers: input vector(s) -> shared memory planes (+ fused RMSNorm), then the stages
   load_x_planes<NB>(p.x, p.ldx, K, p.norm_w, p.eps, xs, s_part, SyncConsumers());
+  XRegs xr = {};
+  const bool use_xr = (NB == 1) && plan.wpu == 1 && (K >> 3) <= 128;
+  if (use_xr) load_xregs(xs, K >> 3, lane, xr);
+  int s = 0;
+  uint32_t ph = 0;
   for (int it = 0; it < total_stages; ++it) {
-    const int s = it % NS;
-    const uint32_t ph = (it / NS) & 1;
     mbar_wait(&full_bar[s], ph);
     const int first = it * ups;
-    gemv_consume_stage<NB>(p, ring + static_cast<size_t>(s) * plan.stage_bytes, xs, red, plan.wpu, first,
+    const int cur = s;
+    gemv_consume_stage<NB>(p, ring + static_cast<size_t>(cur) * plan.stage_bytes, xs, red, plan.wpu, first,
                            min(ups, my_units - first), u_begin, it & 1, [&]() {
-                             if (lane == 0) mbar_arrive(&empty_bar[s]);
-                           });
+                             if (lane == 0) mbar_arrive(&empty_bar[cur]);
+                           }, xr, use_xr);
+    if (++s == NS) s = 0, ph ^= 1;
   }
 }
 

@@ -212,18 +212,26 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     cp_async_commit();
   };
 
+  // ring position of the next stage to consume: slot = g % NS, parity = (g / NS) & 1, kept incrementally (no
+  // integer division in the stage loop)
+  int slot = 0;
+  uint32_t slot_par = 0;
   auto run_stages = [&](const GemvParams& gp, const PhaseSlice& sl, int it0 = 0, int it1 = -1) {
     if (it1 < 0) it1 = sl.stages;
     if (tid == 0 && it0 == 0) prof.mark();  // input vector staged
+    XRegs xr = {};
+    const bool use_xr = (NB == 1) && sl.ups != 1 && (gp.K >> 3) <= 128;
+    if (use_xr) load_xregs(xs, gp.K >> 3, lane, xr);
     for (int it = it0; it < it1; ++it, ++g) {
-      const int slot = g % NS;
-      mbar_wait(&full_bar[slot], (g / NS) & 1);
+      mbar_wait(&full_bar[slot], slot_par);
       if (tid == 0 && (it == 0 || it == sl.stages - 1)) prof.mark();  // first / last stage of the phase has landed
       const int first = it * sl.ups;
-      gemv_consume_stage<NB>(gp, ring + static_cast<size_t>(slot) * P.stage_bytes, xs, red, sl.ups == 1 ? kConsumerWarps : 1, first,
+      const int cur = slot;
+      gemv_consume_stage<NB>(gp, ring + static_cast<size_t>(cur) * P.stage_bytes, xs, red, sl.ups == 1 ? kConsumerWarps : 1, first,
                              min(sl.ups, sl.my_units - first), sl.u_begin, it & 1, [&]() {
-                               if (lane == 0) mbar_arrive(&empty_bar[slot]);
-                             });
+                               if (lane == 0) mbar_arrive(&empty_bar[cur]);
+                             }, xr, use_xr);
+      if (++slot == NS) slot = 0, slot_par ^= 1;
     }
   };
 
