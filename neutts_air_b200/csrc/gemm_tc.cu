@@ -12,6 +12,8 @@
 // Replaces, for the hot path: torch addmm/mm behind transformers modeling_qwen2.py:46-48
 // (MLP), :217-219 (q/k/v), :244 (o_proj), :475 (lm_head) and the codec's Linear / Conv1d
 // layers.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -395,7 +397,11 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, boo
   const int ctas = mt * ((a.N + bn - 1) / bn) * (ep.split_k > 1 ? ep.split_k : 1);
   // two CTAs per SM: grids between one and two waves, and single-row-tile weight streams of many waves (lm_head at
   // batched decode: 1699 tiles), where one CTA's prologue / epilogue overlaps the other's main loop
-  const bool shallow = ctas > num_sms() && (ctas <= 2 * num_sms() || mt == 1);
+  static const bool shallow_all = [] {  // experiment: two CTAs per SM for every multi-wave grid (prefill GEMMs)
+    const char* e = getenv("NT_GEMM_SHALLOW_ALL");
+    return e && e[0] && e[0] != '0';
+  }();
+  const bool shallow = ctas > num_sms() && (ctas <= 2 * num_sms() || mt == 1 || shallow_all);
 #define NT_GEMM_CASE(FMT, BNV)                                                                           \
   return shallow ? launch_gemm<FMT, BNV, true>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)         \
                  : launch_gemm<FMT, BNV, false>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)

@@ -101,26 +101,27 @@ NT_DEVINL void unit_dot(const uint4* r0, const uint4* r1, const float4* xs, int 
   }
 }
 
-// Batch-1 fast path for K <= 1024: the lane's slice of the input vector (chunks lane, lane+32, lane+64, lane+96)
-// stays in registers for the whole phase, so a unit costs two 16-byte shared loads per chunk instead of four, and
+// Batch-1 fast path for warp slices of <= 128 chunks (K <= 1024 per unit, or K <= 8192 split over the 8 warps):
+// the lane's slice of the input vector (chunks c_lo + lane + 32 k, k < 4) stays in registers for the whole phase, so a unit costs two 16-byte shared loads per chunk instead of four, and
 // the fully unrolled loop puts all weight loads of the unit in flight at once.
 struct XRegs {
   float4 a[4], b[4];
 };
-NT_DEVINL void load_xregs(const float4* xs, int nch, int lane, XRegs& xr) {
+NT_DEVINL void load_xregs(const float4* xs, int nch, int c_lo, int c_hi, int lane, XRegs& xr) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int c = lane + 32 * k;
-    const bool ok = c < nch;
+    const int c = c_lo + lane + 32 * k;
+    const bool ok = c < c_hi;
     xr.a[k] = ok ? xs[c] : make_float4(0.f, 0.f, 0.f, 0.f);
     xr.b[k] = ok ? xs[nch + c] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
-NT_DEVINL void unit_dot_x1(const uint4* r0, const uint4* r1, int nch, int lane, const XRegs& xr, float& d0, float& d1) {
+NT_DEVINL void unit_dot_x1(const uint4* r0, const uint4* r1, int c_lo, int c_hi, int lane, const XRegs& xr, float& d0,
+                            float& d1) {
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    const int c = lane + 32 * k;
-    if (c < nch) {
+    const int c = c_lo + lane + 32 * k;
+    if (c < c_hi) {
       float f0[8], f1[8];
       bf16x8_to_f32(r0[c], f0);
       bf16x8_to_f32(r1[c], f1);
@@ -210,7 +211,7 @@ NT_DEVINL void gemv_consume_stage(const GemvParams& p, const uint8_t* st, const 
     if (has) {
       const uint4* r0 = reinterpret_cast<const uint4*>(st + static_cast<size_t>(warp) * unit_bytes);
       if (NB == 1 && use_xr)
-        unit_dot_x1(r0, r0 + nch, nch, lane, xr, d0[0], d1[0]);
+        unit_dot_x1(r0, r0 + nch, 0, nch, lane, xr, d0[0], d1[0]);
       else
         unit_dot<NB>(r0, r0 + nch, xs, nch, 0, nch, lane, d0, d1);
     }
@@ -227,7 +228,10 @@ NT_DEVINL void gemv_consume_stage(const GemvParams& p, const uint8_t* st, const 
   } else {
     const int c_lo = (nch * warp) / kConsumerWarps, c_hi = (nch * (warp + 1)) / kConsumerWarps;
     const uint4* r0 = reinterpret_cast<const uint4*>(st);
-    unit_dot<NB>(r0, r0 + nch, xs, nch, c_lo, c_hi, lane, d0, d1);
+    if (NB == 1 && use_xr)
+      unit_dot_x1(r0, r0 + nch, c_lo, c_hi, lane, xr, d0[0], d1[0]);
+    else
+      unit_dot<NB>(r0, r0 + nch, xs, nch, c_lo, c_hi, lane, d0, d1);
     __syncwarp();
     release();
     float* rbuf = red + parity * (kConsumerWarps * 2 * 4);

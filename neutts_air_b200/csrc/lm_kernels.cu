@@ -122,8 +122,11 @@ __global__ void __launch_bounds__(kGemvThreads, 1) gemv_kernel(const GemvParams 
   // ---- consumers: input vector(s) -> shared memory planes (+ fused RMSNorm), then the stages
   load_x_planes<NB>(p.x, p.ldx, K, p.norm_w, p.eps, xs, s_part, SyncConsumers());
   XRegs xr = {};
-  const bool use_xr = (NB == 1) && plan.wpu == 1 && (K >> 3) <= 128;
-  if (use_xr) load_xregs(xs, K >> 3, lane, xr);
+  const int nch_p = K >> 3;
+  const int xc_lo = plan.wpu == 1 ? 0 : (nch_p * warp) / kConsumerWarps;
+  const int xc_hi = plan.wpu == 1 ? nch_p : (nch_p * (warp + 1)) / kConsumerWarps;
+  const bool use_xr = (NB == 1) && (xc_hi - xc_lo) <= 128;
+  if (use_xr) load_xregs(xs, nch_p, xc_lo, xc_hi, lane, xr);
   int s = 0;
   uint32_t ph = 0;
   for (int it = 0; it < total_stages; ++it) {

@@ -220,8 +220,13 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
     if (it1 < 0) it1 = sl.stages;
     if (tid == 0 && it0 == 0) prof.mark();  // input vector staged
     XRegs xr = {};
-    const bool use_xr = (NB == 1) && sl.ups != 1 && (gp.K >> 3) <= 128;
-    if (use_xr) load_xregs(xs, gp.K >> 3, lane, xr);
+    // the slice of the input this warp multiplies in every stage of the phase: the whole vector when a warp owns
+    // whole units, its eighth of K when the 8 warps share one unit
+    const int nch_p = gp.K >> 3;
+    const int xc_lo = sl.ups == 1 ? (nch_p * warp) / kConsumerWarps : 0;
+    const int xc_hi = sl.ups == 1 ? (nch_p * (warp + 1)) / kConsumerWarps : nch_p;
+    const bool use_xr = (NB == 1) && (xc_hi - xc_lo) <= 128;
+    if (use_xr) load_xregs(xs, nch_p, xc_lo, xc_hi, lane, xr);
     for (int it = it0; it < it1; ++it, ++g) {
       mbar_wait(&full_bar[slot], slot_par);
       if (tid == 0 && (it == 0 || it == sl.stages - 1)) prof.mark();  // first / last stage of the phase has landed
