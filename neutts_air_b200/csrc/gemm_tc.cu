@@ -395,13 +395,15 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, boo
   }
 
   const int ctas = mt * ((a.N + bn - 1) / bn) * (ep.split_k > 1 ? ep.split_k : 1);
-  // two CTAs per SM: grids between one and two waves, and single-row-tile weight streams of many waves (lm_head at
-  // batched decode: 1699 tiles), where one CTA's prologue / epilogue overlaps the other's main loop
-  static const bool shallow_all = [] {  // experiment: two CTAs per SM for every multi-wave grid (prefill GEMMs)
-    const char* e = getenv("NT_GEMM_SHALLOW_ALL");
+  // Two CTAs per SM (half-depth ring) for every grid of more than one wave: one CTA's prologue / epilogue overlaps
+  // the other's main loop, and grids just over a multiple of the SM count lose their short last wave.  Measured at
+  // batch 64: prefill 63 -> 45 ms, codec 36.8 -> 28.8 ms.  NT_GEMM_DEEP_RINGS=1 restores one deep-ring CTA per SM
+  // for grids beyond two waves with several row tiles.
+  static const bool deep_rings = [] {
+    const char* e = getenv("NT_GEMM_DEEP_RINGS");
     return e && e[0] && e[0] != '0';
   }();
-  const bool shallow = ctas > num_sms() && (ctas <= 2 * num_sms() || mt == 1 || shallow_all);
+  const bool shallow = ctas > num_sms() && (ctas <= 2 * num_sms() || mt == 1 || !deep_rings);
 #define NT_GEMM_CASE(FMT, BNV)                                                                           \
   return shallow ? launch_gemm<FMT, BNV, true>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)         \
                  : launch_gemm<FMT, BNV, false>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)
