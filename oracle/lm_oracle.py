@@ -21,7 +21,6 @@ cross-check is the strongest pin available offline.
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass, field
 
 import torch
