@@ -181,8 +181,10 @@ def reference_measure(steps, warmup):
         t = est_full + t_codec
         sample = (f"bounded sample: prefill(500)+1 tok = {t1:.2f}s, 16 decode tokens -> {per_tok * 1e3:.1f} ms/token, codec(250) = "
                   f"{t_codec:.2f}s; composed to 250 tokens, {torch.get_num_threads()} threads")
+    par = [ln.strip() for ln in torch.__config__.parallel_info().splitlines() if "threads" in ln.lower() or "openmp" in ln.lower()]
     return AUDIO_S / t, t * 1e3, sample, cores, dict(prefill_s=t1, ms_per_token=per_tok * 1e3, codec_s=t_codec,
-                                                      decode_tok_s=1.0 / per_tok)
+                                                      decode_tok_s=1.0 / per_tok, torch_threads=torch.get_num_threads(),
+                                                      parallel_info="; ".join(par[:4]))
 
 
 def main_reference(args):
