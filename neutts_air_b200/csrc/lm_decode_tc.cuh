@@ -1,0 +1,77 @@
+// Parameter block + work plan of the persistent tcgen05 decode kernel (lm_decode_tc.cu): ONE cooperative launch
+// runs every layer, the lm_head, the sampler and the whole multi-step decode loop for batch 1..64.
+#pragma once
+#include "lm_kernels.cuh"
+
+struct CUtensorMap_st;
+
+namespace nt {
+
+constexpr int kTcMaxItems = 4;      // work items of one GEMM phase a CTA may own
+constexpr int kTcThreads = 320;     // 8 worker warps + 1 weight-stream warp + 1 MMA warp
+constexpr int kTcMaxBatch = 64;
+constexpr int kTcMaxSlices = 16;
+
+// One GEMM work item: rows [tile*128, tile*128+128) of a weight matrix times k-blocks [kb0, kb0+nkb) of the
+// activations (a k-block = 64 elements = one 128-byte swizzle row).  Items of the split-K phases (qkv, o, down)
+// write raw partial sums into slice `slice`; gate/up items cover the whole K (their epilogue is not linear).
+struct TcItem {
+  short tile, kb0, nkb, slice;
+};
+
+// Per-CTA plan, identical for every layer (the four weight matrices of a layer have the same shape in every
+// layer) + this CTA's contiguous range of lm_head row tiles.  Built on the host (tc_build_plan), read once.
+struct TcPlan {
+  int n[4];                       // items per phase: 0 = qkv, 1 = o_proj, 2 = gate/up, 3 = down
+  TcItem it[4][kTcMaxItems];
+  int head_t0, head_t1;           // lm_head row tiles [t0, t1)
+  int fold_q, fold_g;             // batch <= 4: this CTA writes the folded residual stream back (one CTA per fold point)
+};
+
+struct TcParams {
+  // model
+  int n_layers, total_layers, hidden, inter, n_heads, n_kv, qkv_n, vocab, B;
+  float eps, scale_log2;
+  const CUtensorMap_st* wmaps;    // device [4 * total_layers + 1]: (qkv, o, gate/up, down) per layer, lm_head; box 128 x 64
+  const CUtensorMap_st* xmap;     // xa  [64 rows][hidden] bf16, box NT x 64
+  const CUtensorMap_st* amap;     // act [64 rows][inter]  bf16, box NT x 64
+  const TcPlan* plan;             // device [gridDim.x]
+  const float* const* ln1;
+  const float* const* bqkv;
+  const float* const* ln2;
+  const float* final_norm;
+  const float* inv_freq;
+  // activations
+  float* h;                       // [B][hidden] residual stream (fp32)
+  __nv_bfloat16* xa;              // normalised GEMM input rows: batch <= 8: rows b = hi, 8 + b = lo (bf16 split)
+  __nv_bfloat16* act;             // SwiGLU output rows, same row convention
+  float *part_q, *part_o, *part_d;  // split-K partial sums [slice][B][rows]
+  int sq, so, sd;                 // slices per phase
+  float *att_o, *att_ml;          // split-KV attention partials [B][n_heads][max_splits][64] / [..][2]
+  int max_splits, split_cap;
+  KVLayout kv;
+  float* logits;                  // [B][vocab]
+  float* tmax;                    // [B][ntiles] processed maximum of every 128-row lm_head tile
+  int ntiles;
+  SamplerParams samp;
+  unsigned* gbar;
+  int n_steps;
+  float* logits_out;
+  long long logits_step_stride;
+  long long* prof;
+  int prof_step;
+  // shared-memory plan
+  int nstages;
+  unsigned uni_off, uni_bytes, misc_off;
+  int fold_in_cta;                // 1: batch <= 4, consumers fold the split-K slices themselves (no fold phases)
+};
+
+struct TcShape {  // everything the planner needs
+  int hidden, inter, n_heads, n_kv, qkv_n, vocab;
+};
+// Returns NT_OK and fills plan[G], slices and tile count; NT_ERR_INVALID when the shape does not fit the kernel.
+int tc_build_plan(const TcShape& s, int G, TcPlan* plan, int* sq, int* so, int* sd, int* ntiles, int* max_split_chunks);
+int launch_decode_tc(TcParams& P, int B, int num_sms, int max_split_chunks, cudaStream_t stream);
+size_t tc_smem_bytes(int nt);
+
+}  // namespace nt

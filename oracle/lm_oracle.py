@@ -160,7 +160,8 @@ class KVCache:
 
 
 def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | None = None,
-            collect_hidden: bool = False, mirror: str | None = None, collect: dict | None = None):
+            collect_hidden: bool = False, mirror: str | None = None, collect: dict | None = None,
+            last_only: bool = False):
     """One sequence.  ids: int64 [T] (prompt for prefill, one id for a decode step).
     Follows Qwen2Model.forward modeling_qwen2.py:353-413 and the decoder layer
     :280-309 (pre-norm, residual add after attention and after the MLP); the
@@ -175,7 +176,10 @@ def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | Non
                 attention runs on bf16 tensor-core operands (scaled query and probabilities);
       "batched" (tensor-core decode, batch > 4): as "prefill" plus a bf16 lm_head input.
 
-    Returns (logits [T, V], hiddens list or None).
+    ``last_only`` applies the lm_head to the last position only (what generate needs,
+    modeling_qwen2.py:474-475 ``logits_to_keep``); full-size tests use it to skip a [T, V] product.
+
+    Returns (logits [T, V] (or [1, V]), hiddens list or None).
     """
     cache = cache if cache is not None else KVCache(cfg.num_layers)
     past = cache.length()
@@ -212,7 +216,7 @@ def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | Non
                                h_mid=h_mid.clone(), act=rb(act).clone(), h=h.clone())
         if collect_hidden:
             hiddens.append(h.clone())
-    hn = rms_norm(h, w.final_norm, cfg.rms_eps)                    # :409
+    hn = rms_norm(h[-1:] if last_only else h, w.final_norm, cfg.rms_eps)   # :409
     logits = rb_head(hn) @ w.lm_head.T                             # :475
     return logits, hiddens
 
@@ -256,7 +260,7 @@ def generate(cfg: LMConfig, w: LMWeights, prompt: torch.Tensor, eos_id: int, max
     Returns (generated ids [N], per-step logits [N, V])."""
     g = torch.Generator().manual_seed(seed)
     cache = KVCache(cfg.num_layers)
-    logits, _ = forward(cfg, w, prompt, cache, mirror="prefill" if mirror else None)
+    logits, _ = forward(cfg, w, prompt, cache, mirror="prefill" if mirror else None, last_only=True)
     step_logits, out = [], []
     cur = logits[-1]
     limit = max_length - prompt.shape[0]
