@@ -9,6 +9,9 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda.h>
+
+#include "lm_decode_tc.cuh"
 #include "lm_kernels.cuh"
 #include "lm_mega.cuh"
 
@@ -97,6 +100,13 @@ struct nt_lm {
   int debug_layers = -1;              // >= 0: run only this many layers (per-stage parity tests)
   long long* prof = nullptr;          // megakernel timeline buffer (profiles/probe_mega.py)
   int prof_step = 0;
+  // persistent tcgen05 decode kernel (lm_decode_tc.cu): plan, tensor maps and buffers live in the workspace
+  bool tc_ok = false;
+  int tc_sq = 0, tc_so = 0, tc_sd = 0, tc_ntiles = 0, tc_chunks = 0, tc_rows = 0;
+  uint8_t* tc_maps = nullptr;         // CUtensorMap[4 * n_layers + 1] weights, then xa x {16,32,64}, act x {16,32,64}
+  TcPlan* tc_plan = nullptr;
+  __nv_bfloat16 *tc_xa = nullptr, *tc_act = nullptr;
+  float *tc_part = nullptr, *tc_tmax = nullptr;
 };
 
 template <typename F>
@@ -138,6 +148,13 @@ static size_t lm_carve(const nt_lm_config& c, void* ws, size_t bytes, F&& assign
     (L)->gbar = a.take<unsigned>(256);                                                         \
     (L)->splitk_floats = size_t(8) * 128 * (qkv_n > H ? qkv_n : H);                            \
     (L)->splitk_ws = a.take<float>(size_t(8) * 128 * (qkv_n > H ? qkv_n : H));                 \
+    (L)->tc_rows = c.max_batch < kTcMaxBatch ? c.max_batch : kTcMaxBatch;                      \
+    (L)->tc_maps = a.take<uint8_t>(size_t(128) * (size_t(4) * c.n_layers + 1 + 6));            \
+    (L)->tc_plan = a.take<TcPlan>(256);                                                        \
+    (L)->tc_xa = a.take<__nv_bfloat16>(size_t(kTcMaxBatch) * H);                               \
+    (L)->tc_act = a.take<__nv_bfloat16>(size_t(kTcMaxBatch) * I);                              \
+    (L)->tc_part = a.take<float>(size_t(3) * kTcMaxSlices * (L)->tc_rows * (qkv_n > H ? qkv_n : H)); \
+    (L)->tc_tmax = a.take<float>(size_t((L)->tc_rows) * ((V + 127) / 128));                    \
   }
 
 static int lm_check_config(const nt_lm_config* c) {
@@ -234,6 +251,37 @@ extern "C" int nt_lm_create(const nt_lm_config* cfg, const nt_lm_weights* w, voi
         cudaMemcpy(lm->ptr_tab, pt.data(), pt.size() * sizeof(const float*), cudaMemcpyHostToDevice) != cudaSuccess) {
       delete lm;
       return set_error(NT_ERR_CUDA, "megakernel table upload failed");
+    }
+  }
+  {
+    // persistent tcgen05 decode kernel: work plan + every tensor map, built once (maps were
+    // re-encoded on every GEMM call).  A shape the plan cannot take leaves tc_ok false -> older decode paths.
+    std::vector<TcPlan> plan(256);
+    TcShape ts{c.hidden, c.inter, c.n_heads, c.n_kv_heads, lm->qkv_n, c.vocab_size};
+    const int G = lm->num_sms > 256 ? 256 : lm->num_sms;
+    if (tc_build_plan(ts, G, plan.data(), &lm->tc_sq, &lm->tc_so, &lm->tc_sd, &lm->tc_ntiles, &lm->tc_chunks) == NT_OK) {
+      const size_t nmaps = size_t(4) * c.n_layers + 1 + 6;
+      std::vector<CUtensorMap> maps(nmaps);
+      const int HD = c.n_heads * 64;
+      int mrc = NT_OK;
+      for (int l = 0; l < c.n_layers && !mrc; ++l) {
+        mrc = make_tmap(&maps[4 * l + 0], NT_BF16, lm->wqkv[l], lm->qkv_n, c.hidden, c.hidden, 128);
+        if (!mrc) mrc = make_tmap(&maps[4 * l + 1], NT_BF16, lm->wo[l], c.hidden, HD, HD, 128);
+        if (!mrc) mrc = make_tmap(&maps[4 * l + 2], NT_BF16, lm->wgu[l], 2 * c.inter, c.hidden, c.hidden, 128);
+        if (!mrc) mrc = make_tmap(&maps[4 * l + 3], NT_BF16, lm->wd[l], c.hidden, c.inter, c.inter, 128);
+      }
+      if (!mrc) mrc = make_tmap(&maps[4 * c.n_layers], NT_BF16, lm->lm_head, c.vocab_size, c.hidden, c.hidden, 128);
+      const int nts[3] = {16, 32, 64};
+      for (int i = 0; i < 3 && !mrc; ++i) {
+        mrc = make_tmap(&maps[4 * c.n_layers + 1 + i], NT_BF16, lm->tc_xa, kTcMaxBatch, c.hidden, c.hidden, nts[i]);
+        if (!mrc) mrc = make_tmap(&maps[4 * c.n_layers + 4 + i], NT_BF16, lm->tc_act, kTcMaxBatch, c.inter, c.inter, nts[i]);
+      }
+      static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+      if (!mrc && cudaMemcpy(lm->tc_maps, maps.data(), nmaps * sizeof(CUtensorMap), cudaMemcpyHostToDevice) == cudaSuccess &&
+          cudaMemcpy(lm->tc_plan, plan.data(), 256 * sizeof(TcPlan), cudaMemcpyHostToDevice) == cudaSuccess &&
+          cudaMemset(lm->tc_xa, 0, size_t(kTcMaxBatch) * c.hidden * 2) == cudaSuccess &&
+          cudaMemset(lm->tc_act, 0, size_t(kTcMaxBatch) * c.inter * 2) == cudaSuccess)
+        lm->tc_ok = true;
     }
   }
   bool ok = cudaStreamCreateWithFlags(&lm->cap_stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -502,7 +550,41 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
   if (n_steps < 0) return set_error(NT_ERR_INVALID, "negative step count");
 
   if (n_steps == 0) return NT_OK;
-  if (B <= mega_max_batch() && !env_flag("NT_NO_MEGA") && c.hidden % 64 == 0) {
+  // NT_DECODE_IMPL = tc (default: persistent tcgen05 kernel, every batch size) | mega | perop (round-1 paths, kept
+  // for A/B measurements and as the fallback for shapes the tcgen05 plan does not take)
+  const char* impl = getenv("NT_DECODE_IMPL");
+  const bool want_tc = !impl || !impl[0] || impl[0] == 't';
+  const int tc_layers = lm->debug_layers >= 0 ? lm->debug_layers : c.n_layers;
+  if (want_tc && lm->tc_ok && B <= lm->tc_rows && B * c.n_kv_heads <= lm->num_sms && !env_flag("NT_NO_MEGA")) {
+    TcParams P;
+    memset(&P, 0, sizeof(P));
+    P.n_layers = tc_layers, P.total_layers = c.n_layers;
+    P.hidden = c.hidden, P.inter = c.inter, P.n_heads = c.n_heads, P.n_kv = c.n_kv_heads, P.qkv_n = lm->qkv_n, P.vocab = c.vocab_size;
+    P.eps = c.rms_eps, P.scale_log2 = (1.0f / 8.0f) * 1.4426950408889634f;
+    const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(lm->tc_maps);
+    const int nti = B <= 16 ? 0 : (B <= 32 ? 1 : 2);
+    P.wmaps = maps, P.xmap = maps + 4 * c.n_layers + 1 + nti, P.amap = maps + 4 * c.n_layers + 4 + nti;
+    P.plan = lm->tc_plan;
+    P.ln1 = lm->ptr_tab, P.bqkv = lm->ptr_tab + c.n_layers, P.ln2 = lm->ptr_tab + 2 * c.n_layers;
+    P.final_norm = lm->final_norm, P.inv_freq = lm->inv_freq;
+    P.h = lm->h, P.xa = lm->tc_xa, P.act = lm->tc_act;
+    const size_t pstride = size_t(kTcMaxSlices) * lm->tc_rows * (lm->qkv_n > c.hidden ? lm->qkv_n : c.hidden);
+    P.part_q = lm->tc_part, P.part_o = lm->tc_part + pstride, P.part_d = lm->tc_part + 2 * pstride;
+    P.sq = lm->tc_sq, P.so = lm->tc_so, P.sd = lm->tc_sd;
+    P.att_o = lm->part_o, P.att_ml = lm->part_ml, P.max_splits = lm->max_splits;
+    P.kv = make_kv(lm, st);
+    P.logits = lm->logits, P.tmax = lm->tc_tmax, P.ntiles = lm->tc_ntiles;
+    P.samp = make_sampler(lm, st, sp);
+    P.samp.advance = 1;
+    P.gbar = lm->gbar;
+    P.n_steps = n_steps;
+    P.logits_out = logits_out;
+    P.logits_step_stride = static_cast<long long>(B) * c.vocab_size;
+    P.prof = lm->prof, P.prof_step = lm->prof_step;
+    if ((rc = launch_sampler_check(P.samp))) return rc;
+    return launch_decode_tc(P, B, lm->num_sms > 256 ? 256 : lm->num_sms, lm->tc_chunks, stream);
+  }
+  if (B <= mega_max_batch() && !env_flag("NT_NO_MEGA") && !(impl && impl[0] == 'p') && c.hidden % 64 == 0) {
     // Persistent megakernel: every layer, the lm_head, the sampler and all n_steps in one launch.
     // It wins up to 4 sequences (0.86 ms / step at batch 1 against 1.65 ms for the per-op chain, whose step time
     // is the same from batch 5 to 64).  NT_MEGA_MAX_BATCH=5..16 instead runs up to four concurrent instances of

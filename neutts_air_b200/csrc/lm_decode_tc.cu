@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
     };
     auto write_back_h = [&] {  // the designated CTA publishes the folded residual stream (after the phase's barrier)
       for (int e = tid; e < B * H; e += kConsumerThreads) P.h[e] = xf[e];
+      csync();  // xf lies in the union region: nobody may reuse it before every thread has read its part
     };
 
     // ---- attention item of this CTA: (sequence, kv head, split)
@@ -671,12 +672,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       const int b = blockIdx.x;
       if (b >= B) return;
       const int nt = P.ntiles, V = P.vocab;
-      uint32_t* keys = reinterpret_cast<uint32_t*>(uni);
-      uint32_t* scratch = keys + ((nt + 31) & ~31);
+      uint32_t* scratch = reinterpret_cast<uint32_t*>(uni);
       int* tiles = reinterpret_cast<int*>(scratch + kSelScratch);   // [64] chosen tiles
       int* counts = tiles + 64;                                      // [64] candidates per chosen tile, then offsets
       Cand* win = reinterpret_cast<Cand*>(counts + 64);              // [2 * kTopKeep]
       int* s_tok = reinterpret_cast<int*>(win + 2 * kTopKeep);
+      uint32_t* keys = reinterpret_cast<uint32_t*>(s_tok + 4);       // the rest of the union region
+      const int key_cap = static_cast<int>((P.uni_bytes - (kSelScratch + 128 + 4) * 4 - 2 * kTopKeep * sizeof(Cand)) / 4);
       const float inv_t = 1.0f / P.samp.sp.temperature;
       const bool mask_eos = ms->mask_eos[b] != 0;
       const int eos = P.samp.sp.eos_id;
@@ -687,6 +689,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       uint32_t thr;
       int take_eq;
       radix_select_kth(keys, nt, k, scratch, thr, take_eq, csync);
+      // fewer tiles than top_k: the tile maxima bound nothing, every logit of every tile is a candidate
+      const uint32_t cthr = nt < P.samp.sp.top_k ? 1u : thr;
       // the k tiles: maxima above the threshold, then the first take_eq tiles (index order) that equal it
       compact_topk(keys, nt, thr, take_eq, scratch, csync, [&](int slot, int i) { tiles[slot] = i; });
       csync();
@@ -712,7 +716,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         tile_keys(tiles[j], kk);
         int c = 0;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) c += __popc(__ballot_sync(0xffffffffu, kk[q] >= thr && kk[q] != 0u));
+        for (int q = 0; q < 4; ++q) c += __popc(__ballot_sync(0xffffffffu, kk[q] >= cthr && kk[q] != 0u));
         if (lane == 0) counts[j] = c;
       }
       csync();
@@ -731,10 +735,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         if (lane == 0) ms->sel[0] = tot;
       }
       csync();
-      const int ncand = ms->sel[0];
+      const int ncand = min(min(ms->sel[0], key_cap), 256 * kTopKeep);   // beyond: thousands of exact ties at the threshold
       // pass 2: write the candidates at their deterministic offsets (layout sample_stage2_seq expects: [b * ncand + i])
-      float* cv = P.samp.cand_val + static_cast<long long>(b) * ncand;
-      int32_t* ci = P.samp.cand_idx + static_cast<long long>(b) * ncand;
+      constexpr long long kCandPitch = 256 * kTopKeep;   // row pitch of the candidate arrays (sampler_scratch_floats)
+      float* cv = P.samp.cand_val + static_cast<long long>(b) * kCandPitch;
+      int32_t* ci = P.samp.cand_idx + static_cast<long long>(b) * kCandPitch;
       for (int j = warp; j < k; j += kConsumerWarps) {
         uint32_t kk[4];
         const int tile = tiles[j];
@@ -742,18 +747,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         int base = counts[j];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const bool hit = kk[q] >= thr && kk[q] != 0u;
+          const bool hit = kk[q] >= cthr && kk[q] != 0u;
           const uint32_t m = __ballot_sync(0xffffffffu, hit);
           if (hit) {
             const int o = base + __popc(m & ((1u << lane) - 1u));
-            cv[o] = key2f(kk[q]);
-            ci[o] = tile * 128 + lane * 4 + q;
+            if (o < ncand) {
+              cv[o] = key2f(kk[q]);
+              ci[o] = tile * 128 + lane * 4 + q;
+            }
           }
           base += __popc(m);
         }
       }
       csync();
-      sample_stage2_seq(P.samp, b, ncand, keys, scratch, win, s_tok, csync);
+      sample_stage2_seq(P.samp, b, ncand, keys, scratch, win, s_tok, csync, NoMark(), kCandPitch);
     };
 
     // =============================================================== the decode loop
@@ -771,8 +778,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       }
       csync();
       if (!fold_cta) {
-        fold_phase(nullptr, 0, H, P.ln1[0]);
-        grid_sync([&] { load_bop_split(xmap, kPhQ); });
+        fold_phase(nullptr, 0, H, L > 0 ? P.ln1[0] : P.final_norm);
+        if (L > 0) grid_sync([&] { load_bop_split(xmap, kPhQ); });
+        else grid_sync([&] { load_bop_full(xmap, n_head_tiles > 0); });
       }
       for (int l = 0; l < L; ++l) {
         // ---- qkv

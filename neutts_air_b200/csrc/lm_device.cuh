@@ -679,13 +679,15 @@ struct NoMark {
 };
 template <typename Sync, typename Mark = NoMark>
 NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint32_t* keys, uint32_t* scratch, Cand* win, int* s_tok,
-                                 Sync sync, Mark mark = Mark()) {
+                                 Sync sync, Mark mark = Mark(), long long cand_stride = -1) {
   const int tid = threadIdx.x;
   const bool stateless = p.n_generated_override != nullptr;
   const int ngen = stateless ? __ldcg(p.n_generated_override + b) : __ldcg(p.n_generated + b);
   const bool is_done = stateless ? false : (__ldcg(p.done + b) != 0);
-  const float* cv = p.cand_val + static_cast<long long>(b) * ncand;
-  const int32_t* ci = p.cand_idx + static_cast<long long>(b) * ncand;
+  // candidate rows: [b * stride, b * stride + ncand); stride = ncand unless the caller's rows have their own pitch
+  const long long cstride = cand_stride >= 0 ? cand_stride : static_cast<long long>(ncand);
+  const float* cv = p.cand_val + static_cast<long long>(b) * cstride;
+  const int32_t* ci = p.cand_idx + static_cast<long long>(b) * cstride;
   Cand* raw = win + kTopKeep;  // unsorted winners
   sync();
   for (int e0 = 0; e0 < ncand; e0 += 8 * kConsumerThreads) {  // 8 independent loads in flight per thread

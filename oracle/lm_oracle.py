@@ -252,11 +252,13 @@ def topk_probs(logits: torch.Tensor, n_generated: int, eos_id: int, min_new_toke
 def generate(cfg: LMConfig, w: LMWeights, prompt: torch.Tensor, eos_id: int, max_length: int = 2048,
              min_new_tokens: int = 50, temperature: float = 1.0, top_k: int = 50,
              max_new_tokens: int | None = None, seed: int = 0, forced: torch.Tensor | None = None,
-             mirror: bool = False):
+             mirror: bool = False, decode_mirror: str | None = None):
     """The hot loop generation/utils.py:2743-2805 for one sequence: prefill, then
     decode one token at a time until EOS (after min_new_tokens) or max_length
     (prompt + generated, stopping_criteria.py:73-84).  ``forced`` teacher-forces
     the emitted tokens (for logits parity; sampling RNG streams cannot match).
+    ``mirror`` applies the CUDA path's stated rounding points ("prefill" for the prompt, "decode" for the
+    steps; ``decode_mirror="batched"`` selects the batch > 8 decode roundings instead).
     Returns (generated ids [N], per-step logits [N, V])."""
     g = torch.Generator().manual_seed(seed)
     cache = KVCache(cfg.num_layers)
@@ -278,7 +280,8 @@ def generate(cfg: LMConfig, w: LMWeights, prompt: torch.Tensor, eos_id: int, max
             break
         if len(out) >= limit:
             break
-        logits, _ = forward(cfg, w, torch.tensor([tok]), cache, mirror="decode" if mirror else None)
+        logits, _ = forward(cfg, w, torch.tensor([tok]), cache,
+                            mirror=decode_mirror if decode_mirror else ("decode" if mirror else None))
         cur = logits[-1]
     return torch.tensor(out, dtype=torch.int64), torch.stack(step_logits)
 
