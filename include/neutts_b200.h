@@ -42,7 +42,7 @@ typedef enum {
 
 const char* nt_last_error(void);
 /* library/ABI version, bumped on any signature change */
-int nt_abi_version(void);
+int nt_abi_version(void);   /* 2: nt_sampling gained limits + slot_base */
 /* number of kernels launched by this library since load (all streams); bench.py reports the delta */
 uint64_t nt_launch_count(void);
 
@@ -133,6 +133,9 @@ typedef struct {
   uint64_t seed;
   int32_t greedy;           /* 1: argmax instead of sampling (tests) */
   const int32_t* forced;    /* optional [max_batch][max_new] teacher-forced tokens (tests), else NULL */
+  const int32_t* limits;    /* optional device [max_batch]: per-sequence cap on generated tokens (transformers'
+                               max_length is prompt + generated PER SEQUENCE, stopping_criteria.py:73-84), else NULL */
+  int32_t slot_base;        /* global index of slot 0: keys the Philox stream, so chunks / ranks draw independently */
 } nt_sampling;
 
 typedef struct nt_lm nt_lm;

@@ -58,9 +58,14 @@ class _CrossFade:
 
 
 class NeuTTS:
-    def __init__(self, backbone_repo="neuphonic/neutts-nano", backbone_device="cuda", codec_repo="neuphonic/neucodec",
-                 codec_device="cuda", *, tokenizer=None, phonemizer=None, backbone=None, codec=None,
+    def __init__(self, backbone_repo="neuphonic/neutts-nano", backbone_device="cpu", codec_repo="neuphonic/neucodec",
+                 codec_device="cpu", *, tokenizer=None, phonemizer=None, backbone=None, codec=None,
                  max_batch: int = 1, seed: int | None = None):
+        """Same positional signature and defaults as the reference (``neutts/neutts.py:75-81``), so
+        ``examples/basic_example.py:12-17`` runs unmodified.  The device strings keep their reference
+        meaning for the CALLER -- ``"cpu"`` = results come back as host arrays, which this facade always
+        does -- but the engines themselves only exist for sm_100a: a ``"cpu"`` request runs on the current
+        CUDA device and says so once (there is no CPU fallback)."""
         # constants the reference exposes (neutts/neutts.py:84-91)
         self.sample_rate = 24_000
         self.max_context = 2048
@@ -104,8 +109,7 @@ class NeuTTS:
         if str(backbone_repo).endswith("gguf"):
             raise ValueError("GGUF / llama.cpp backbones are not dispatched by the B200 build; "
                              "use the safetensors checkpoint (e.g. neuphonic/neutts-air)")
-        if torch.device(backbone_device).type != "cuda":
-            raise ValueError("neutts (B200 build) runs the backbone on CUDA only; got backbone_device=%r" % (backbone_device,))
+        backbone_device = self._engine_device(backbone_device, "backbone")
         from neutts_air_b200 import loader
 
         if self.tokenizer is None:
@@ -122,12 +126,26 @@ class NeuTTS:
         if codec_repo not in ("neuphonic/neucodec", "neuphonic/distill-neucodec") and not Path(str(codec_repo)).exists():
             raise ValueError("Invalid codec repo! Must be one of: 'neuphonic/neucodec', 'neuphonic/distill-neucodec' "
                              "(or a local checkpoint directory).")
-        if torch.device(codec_device).type != "cuda":
-            raise ValueError("neutts (B200 build) runs the codec on CUDA only; got codec_device=%r" % (codec_device,))
+        codec_device = self._engine_device(codec_device, "codec")
         from neutts_air_b200 import loader
 
         self.codec = loader.load_codec_decoder(codec_repo, codec_device, max_batch=self.max_batch,
                                                max_frames=self.max_context)
+
+    @staticmethod
+    def _engine_device(requested, what: str):
+        """Reference device string -> the CUDA device the B200 engine runs on."""
+        dev = torch.device(requested)
+        if dev.type == "cuda":
+            return dev
+        if dev.type != "cpu":
+            raise ValueError(f"unsupported {what}_device {requested!r}")
+        if not torch.cuda.is_available():
+            raise RuntimeError(f"neutts (B200 build): {what}_device={requested!r} was requested, but the engines exist only for "
+                               "CUDA sm_100a and no CUDA device is visible (there is no CPU fallback)")
+        warnings.warn(f"neutts (B200 build): {what}_device={requested!r} -> running on cuda:{torch.cuda.current_device()}; "
+                      "outputs are returned on the host as with the reference's CPU path", stacklevel=3)
+        return torch.device("cuda", torch.cuda.current_device())
 
     # ------------------------------------------------------------------ prompt construction (N1)
     def _to_phones(self, text: str) -> str:
@@ -163,14 +181,15 @@ class NeuTTS:
 
     # ------------------------------------------------------------------ hot path A
     def _generate_ids(self, prompts: Sequence[Sequence[int]], max_new_tokens: int | None = None,
-                      min_new_tokens: int = 50) -> list:
+                      min_new_tokens: int = 50, slot_base: int = 0) -> list:
         """Batched device-side generation; returns generated token ids per prompt (CPU int64 tensors).
         Sampling parameters are the reference's (``neutts/neutts.py:338-347``)."""
         eos = self._tok_id("<|SPEECH_GENERATION_END|>")
         seed = self.seed if self.seed is not None else int(torch.randint(0, 2**31 - 1, (1,)).item())
         if hasattr(self.backbone, "generate_batch"):
             return self.backbone.generate_batch(list(prompts), eos, max_length=self.max_context, min_new_tokens=min_new_tokens,
-                                                temperature=1.0, top_k=50, max_new_tokens=max_new_tokens, seed=seed)
+                                                temperature=1.0, top_k=50, max_new_tokens=max_new_tokens, seed=seed,
+                                                slot_base=slot_base)
         outs = []  # injected transformers-style backbone: one sequence at a time, as the reference does
         for p in prompts:
             t = torch.tensor(list(p)).unsqueeze(0).to(self.backbone.device)
@@ -232,9 +251,10 @@ class NeuTTS:
         return self.infer_batch([text], [ref_codes], [ref_text])[0]
 
     def infer_from_prompt_ids(self, prompts: Sequence[Sequence[int]], max_new_tokens: int | None = None,
-                              min_new_tokens: int = 50) -> list:
-        """Hot path only: prompt ids (host) -> waveforms (host).  Used by bench.py's end-to-end leg."""
-        gen = self._generate_ids(prompts, max_new_tokens, min_new_tokens)
+                              min_new_tokens: int = 50, slot_base: int = 0) -> list:
+        """Hot path only: prompt ids (host) -> waveforms (host).  Used by bench.py's end-to-end leg.
+        ``slot_base`` offsets the sampler's Philox slot index so chunks / ranks under one seed draw independently."""
+        gen = self._generate_ids(prompts, max_new_tokens, min_new_tokens, slot_base)
         return [self._watermark(w) for w in self._decode_codes([self._ids_to_codes(g) for g in gen])]
 
     def infer_batch(self, texts: Sequence[str], ref_codes: Sequence, ref_texts: Sequence[str], distributed: bool = False) -> list:
@@ -246,14 +266,15 @@ class NeuTTS:
         if not distributed:
             out = []
             for j in range(0, len(prompts), self.max_batch):
-                out += self.infer_from_prompt_ids(prompts[j: j + self.max_batch])
+                out += self.infer_from_prompt_ids(prompts[j: j + self.max_batch], slot_base=j)
             return out
         from neutts_air_b200 import dist
 
         mine = dist.shard_indices(len(prompts), [len(p) for p in prompts])
         local = []
+        rank = dist.world()[0]
         for j in range(0, len(mine), self.max_batch):
-            local += self.infer_from_prompt_ids([prompts[i] for i in mine[j: j + self.max_batch]])
+            local += self.infer_from_prompt_ids([prompts[i] for i in mine[j: j + self.max_batch]], slot_base=(rank << 20) + j)
         return dist.all_gather_waveforms(local, mine, len(prompts), device=self.codec.device)
 
     def infer_stream(self, text: str, ref_codes, ref_text: str) -> Generator[np.ndarray, None, None]:
@@ -320,10 +341,17 @@ class NeuTTS:
             return torch.from_numpy(np.load(p))
         try:
             import librosa
+
+            wav, _ = librosa.load(ref_audio_path, sr=16000, mono=True)
+            wav_tensor = torch.from_numpy(wav).float().unsqueeze(0).unsqueeze(0)
+            with torch.no_grad():
+                return self.codec.encode_code(audio_or_path=wav_tensor).squeeze(0).squeeze(0)
         except ImportError as e:
-            raise ImportError("librosa is required to read reference audio; alternatively pass pre-encoded codes "
-                              "(samples/*.pt)") from e
-        wav, _ = librosa.load(ref_audio_path, sr=16000, mono=True)
-        wav_tensor = torch.from_numpy(wav).float().unsqueeze(0).unsqueeze(0)
-        with torch.no_grad():
-            return self.codec.encode_code(audio_or_path=wav_tensor).squeeze(0).squeeze(0)
+            # neither librosa nor the neucodec encoder is installed: use the pre-encoded codes that sit next to
+            # the audio (the reference ships samples/dave.wav + samples/dave.pt, examples/README.md:15-23)
+            for ext in (".pt", ".npy"):
+                q = p.with_suffix(ext)
+                if q.exists():
+                    warnings.warn(f"{e}; using the pre-encoded reference codes {q.name}")
+                    return torch.load(q) if ext == ".pt" else torch.from_numpy(np.load(q))
+            raise ImportError(f"cannot encode {p.name}: {e} (and no pre-encoded {p.stem}.pt / .npy next to it)") from e

@@ -56,7 +56,7 @@ class Sampling(C.Structure):
     _fields_ = [
         ("eos_id", C.c_int32), ("min_new_tokens", C.c_int32), ("max_new_tokens", C.c_int32),
         ("top_k", C.c_int32), ("temperature", C.c_float), ("seed", C.c_uint64), ("greedy", C.c_int32),
-        ("forced", C.c_void_p),
+        ("forced", C.c_void_p), ("limits", C.c_void_p), ("slot_base", C.c_int32),
     ]
 
 

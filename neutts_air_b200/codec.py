@@ -125,25 +125,43 @@ class CodecDecoder:
         return self
 
     @torch.no_grad()
-    def decode_code(self, codes: torch.Tensor) -> torch.Tensor:
-        """codes: integer [B, 1, N] (values in [0, levels**dims)) -> float32 [B, 1, hop*N] on ``self.device``."""
+    def decode_code(self, codes: torch.Tensor, validate: bool | None = None) -> torch.Tensor:
+        """codes: integer [B, 1, N] (values in [0, levels**dims)) -> float32 [B, 1, hop*N] on ``self.device``.
+
+        Range validation needs the values on the host: it runs for CPU inputs (free) and is skipped for CUDA
+        inputs unless ``validate=True`` (a min/max read-back is a device synchronisation inside the hot path;
+        the kernel itself never reads out of bounds on a bad id, it decodes the id modulo the codebook)."""
         if codes.dim() != 3 or codes.shape[1] != 1:
             raise ValueError("codes must be [B, 1, N]")
         B, _, N = codes.shape
         if N < 1:
             raise ValueError("No valid speech tokens found in the output.")
         cmax = self.shape.fsq_levels ** self.shape.fsq_dims
+        if validate is None:
+            validate = codes.device.type == "cpu"
+        if validate and (int(codes.min()) < 0 or int(codes.max()) >= cmax):
+            raise ValueError(f"codec ids must be in [0, {cmax})")
         with torch.cuda.device(self.device):
             c32 = codes[:, 0, :].to(self.device, torch.int32).contiguous()
-            if int(c32.min()) < 0 or int(c32.max()) >= cmax:
-                raise ValueError(f"codec ids must be in [0, {cmax})")
             pcm = torch.empty(B, 1, self.shape.hop * N, dtype=torch.float32, device=self.device)
             _lib.check(self.L.nt_codec_decode(self.handle, c32.data_ptr(), B, N, pcm.data_ptr(), _lib.current_stream_ptr()))
         return pcm
 
     def encode_code(self, audio_or_path):
-        """The encoder half (wav -> codes) is outside the hot path (one-off per speaker,
-        pre-encodable).  Delegates to the real ``neucodec`` package when it is installed."""
-        raise NotImplementedError(
-            "neutts_air_b200 implements the NeuCodec *decoder*; encode references with `neucodec` "
-            "(examples/encode_reference.py) and pass the saved codes")
+        """The encoder half (wav -> codes, ``neutts/neutts.py:266-271``) is outside the hot path (SURVEY.md §2:
+        one-off per speaker, pre-encodable), so it is not reimplemented: this delegates to the real ``neucodec``
+        package (lazily loaded on first use, kept on this decoder's GPU) and raises ImportError with the
+        pre-encoding recipe when it is not installed."""
+        if getattr(self, "_encoder", None) is None:
+            try:
+                from neucodec import DistillNeuCodec, NeuCodec
+            except ImportError as e:
+                raise ImportError(
+                    "encoding reference audio needs the `neucodec` package (pip install neucodec): neutts_air_b200 "
+                    "implements the NeuCodec *decoder* only. Alternatively pre-encode the reference once with "
+                    "examples/encode_reference.py and pass the saved .pt codes to NeuTTS.infer / encode_reference") from e
+            repo = getattr(self, "repo", None) or "neuphonic/neucodec"
+            cls = DistillNeuCodec if "distill" in str(repo) else NeuCodec
+            self._encoder = cls.from_pretrained(repo).eval().to(self.device)
+        with torch.no_grad():
+            return self._encoder.encode_code(audio_or_path=audio_or_path)

@@ -106,7 +106,10 @@ struct nt_lm {
   uint8_t* tc_maps = nullptr;         // CUtensorMap[4 * n_layers + 1] weights, then xa x {16,32,64}, act x {16,32,64}
   TcPlan* tc_plan = nullptr;
   __nv_bfloat16 *tc_xa = nullptr, *tc_act = nullptr;
-  float *tc_part = nullptr, *tc_tmax = nullptr;
+  float *tc_tmax = nullptr;
+  float2 *tc_pq2 = nullptr, *tc_po2 = nullptr, *tc_pd2 = nullptr, *tc_ao2 = nullptr, *tc_aml2 = nullptr, *tc_act2 = nullptr, *tc_h2 = nullptr;
+  size_t tc_pair_bytes = 0;           // extent of the stamped buffers (contiguous, starting at tc_pq2)
+  int tc_stamp = 0, tc_hstamp = 0;    // stamps handed out so far (see TcParams::stamp_base)
 };
 
 template <typename F>
@@ -153,8 +156,15 @@ static size_t lm_carve(const nt_lm_config& c, void* ws, size_t bytes, F&& assign
     (L)->tc_plan = a.take<TcPlan>(256);                                                        \
     (L)->tc_xa = a.take<__nv_bfloat16>(size_t(kTcMaxBatch) * H);                               \
     (L)->tc_act = a.take<__nv_bfloat16>(size_t(kTcMaxBatch) * I);                              \
-    (L)->tc_part = a.take<float>(size_t(3) * kTcMaxSlices * (L)->tc_rows * (qkv_n > H ? qkv_n : H)); \
     (L)->tc_tmax = a.take<float>(size_t((L)->tc_rows) * ((V + 127) / 128));                    \
+    (L)->tc_pq2 = a.take<float2>(size_t(kTcMaxSlices) * (L)->tc_rows * qkv_n);                 \
+    (L)->tc_po2 = a.take<float2>(size_t(kTcMaxSlices) * (L)->tc_rows * H);                     \
+    (L)->tc_pd2 = a.take<float2>(size_t(kTcMaxSlices) * (L)->tc_rows * H);                     \
+    (L)->tc_ao2 = a.take<float2>(size_t((L)->tc_rows) * c.n_heads * max_splits * 64);          \
+    (L)->tc_aml2 = a.take<float2>(size_t((L)->tc_rows) * c.n_heads * max_splits * 2);          \
+    (L)->tc_act2 = a.take<float2>(size_t(4) * I);                                              \
+    (L)->tc_h2 = a.take<float2>(size_t(2) * 4 * H);                                            \
+    (L)->tc_pair_bytes = size_t(reinterpret_cast<uint8_t*>((L)->tc_h2 + size_t(2) * 4 * H) - reinterpret_cast<uint8_t*>((L)->tc_pq2)); \
   }
 
 static int lm_check_config(const nt_lm_config* c) {
@@ -171,7 +181,7 @@ static int lm_check_config(const nt_lm_config* c) {
 }
 
 extern "C" const char* nt_last_error(void) { return g_err; }
-extern "C" int nt_abi_version(void) { return 1; }
+extern "C" int nt_abi_version(void) { return 2; }
 extern "C" uint64_t nt_launch_count(void) { return g_launches.load(); }
 
 extern "C" size_t nt_lm_workspace_bytes(const nt_lm_config* cfg) {
@@ -280,7 +290,8 @@ extern "C" int nt_lm_create(const nt_lm_config* cfg, const nt_lm_weights* w, voi
       if (!mrc && cudaMemcpy(lm->tc_maps, maps.data(), nmaps * sizeof(CUtensorMap), cudaMemcpyHostToDevice) == cudaSuccess &&
           cudaMemcpy(lm->tc_plan, plan.data(), 256 * sizeof(TcPlan), cudaMemcpyHostToDevice) == cudaSuccess &&
           cudaMemset(lm->tc_xa, 0, size_t(kTcMaxBatch) * c.hidden * 2) == cudaSuccess &&
-          cudaMemset(lm->tc_act, 0, size_t(kTcMaxBatch) * c.inter * 2) == cudaSuccess)
+          cudaMemset(lm->tc_act, 0, size_t(kTcMaxBatch) * c.inter * 2) == cudaSuccess &&
+          cudaMemset(lm->tc_pq2, 0, lm->tc_pair_bytes) == cudaSuccess)   // stamp 0 = "never written"
         lm->tc_ok = true;
     }
   }
@@ -344,6 +355,7 @@ static SamplerParams make_sampler(const nt_lm* lm, const nt_lm_state* st, const 
   s.embed = lm->embed;
   s.h = lm->h;
   s.hidden = lm->cfg.hidden;
+  s.slot_base = sp->slot_base;
   return s;
 }
 
@@ -568,11 +580,20 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
     P.ln1 = lm->ptr_tab, P.bqkv = lm->ptr_tab + c.n_layers, P.ln2 = lm->ptr_tab + 2 * c.n_layers;
     P.final_norm = lm->final_norm, P.inv_freq = lm->inv_freq;
     P.h = lm->h, P.xa = lm->tc_xa, P.act = lm->tc_act;
-    const size_t pstride = size_t(kTcMaxSlices) * lm->tc_rows * (lm->qkv_n > c.hidden ? lm->qkv_n : c.hidden);
-    P.part_q = lm->tc_part, P.part_o = lm->tc_part + pstride, P.part_d = lm->tc_part + 2 * pstride;
+    P.pq2 = lm->tc_pq2, P.po2 = lm->tc_po2, P.pd2 = lm->tc_pd2;
     P.sq = lm->tc_sq, P.so = lm->tc_so, P.sd = lm->tc_sd;
-    P.att_o = lm->part_o, P.att_ml = lm->part_ml, P.max_splits = lm->max_splits;
+    P.ao2 = lm->tc_ao2, P.aml2 = lm->tc_aml2, P.act2 = lm->tc_act2, P.h2 = lm->tc_h2, P.max_splits = lm->max_splits;
+    // (value, stamp) hand-offs: every launch takes a fresh range of stamps, so nothing left in the buffers by an
+    // earlier launch (or by another batch size) can ever match
+    const int need_s = n_steps * (tc_layers + 1) + 2, need_h = n_steps * (2 * tc_layers + 1) + 4;
+    if (lm->tc_stamp > 0x7fff0000 - need_s || lm->tc_hstamp > 0x7fff0000 - need_h) {
+      NT_CUDA_CHECK(cudaMemsetAsync(lm->tc_pq2, 0, lm->tc_pair_bytes, stream));
+      lm->tc_stamp = lm->tc_hstamp = 0;
+    }
+    P.stamp_base = lm->tc_stamp, P.hstamp_base = lm->tc_hstamp;
+    lm->tc_stamp += need_s, lm->tc_hstamp += need_h;
     P.kv = make_kv(lm, st);
+    if ((rc = kv_pool_tmap(P.kv, c.n_layers, &P.kvmap))) return rc;
     P.logits = lm->logits, P.tmax = lm->tc_tmax, P.ntiles = lm->tc_ntiles;
     P.samp = make_sampler(lm, st, sp);
     P.samp.advance = 1;
@@ -618,7 +639,7 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
       P.counters = lm->counters, P.max_splits = lm->max_splits;
       P.samp = make_sampler(lm, st, sp);
       P.samp.advance = 1;
-      P.samp.slot_base = b0;
+      P.samp.slot_base = sp->slot_base + b0;
       P.samp.logits = P.logits;
       P.samp.seq_lens += b0, P.samp.cur_token += b0, P.samp.n_generated += b0, P.samp.done += b0;
       P.samp.out_tokens += size_t(b0) * st->max_new;

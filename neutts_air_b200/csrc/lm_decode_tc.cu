@@ -56,14 +56,29 @@ NT_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// (value, stamp) pairs: relaxed gpu-scope loads (served by L2, never by a stale L1 line)
+NT_DEVINL float4 ldp2(const float2* p) {
+  float4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+NT_DEVINL float2 ldp1(const float2* p) {
+  float2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+NT_DEVINL uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
 NT_DEVINL void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 NT_DEVINL void bar_epi() { asm volatile("bar.sync 2, 128;" ::: "memory"); }  // the four epilogue warps
 
-struct TcProf {
+struct TcProf {   // timeline of one CTA: buf[n] = %globaltimer, buf[512 + n] = mark id
   long long* buf;
   int n;
-  NT_DEVINL void mark() {
-    if (buf && n < 1024) buf[n++] = tc_ns();
+  bool fine;     // fine-grained marks on (one chosen layer)
+  NT_DEVINL void mark(int id = 0) {
+    if (buf && n < 512) buf[n] = tc_ns(), buf[512 + n] = id, ++n;
   }
 };
 
@@ -77,7 +92,59 @@ NT_DEVINL __nv_bfloat16* chunk_elem(uint8_t* chunk, int n, int k) {
   return reinterpret_cast<__nv_bfloat16*>(chunk + n * 128 + ((((k >> 3) ^ (n & 7)) << 4) | ((k & 7) << 1)));
 }
 
+
+NT_DEVINL void tc_spin_check(uint32_t& spins, const char* what) {
+  if (++spins > (1u << 22)) {
+    printf("neutts_b200: decode_tc poll timed out waiting for %s (block %d thread %d)\n", what, blockIdx.x, threadIdx.x);
+    __trap();
+  }
+}
+
+// 4 consecutive elements of row b: residual pairs (or nothing) + the split-K slices in slice order; polls the stamps
+NT_DEVINL void tc_fold4(const float2* hsrc, int hstamp, const float2* parts, int nparts, int pstamp, int rows, int B, int H, int b,
+                        int i4, float (&acc)[4]) {
+  acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+  if (hsrc) {
+    uint32_t spins = 0;
+    for (;;) {
+      const float4 a0 = ldp2(hsrc + static_cast<long long>(b) * H + i4), a1 = ldp2(hsrc + static_cast<long long>(b) * H + i4 + 2);
+      if (__float_as_int(a0.y) == hstamp && __float_as_int(a0.w) == hstamp && __float_as_int(a1.y) == hstamp &&
+          __float_as_int(a1.w) == hstamp) {
+        acc[0] = a0.x, acc[1] = a0.z, acc[2] = a1.x, acc[3] = a1.z;
+        break;
+      }
+      tc_spin_check(spins, "the residual stream");
+    }
+  }
+  for (int s0 = 0; s0 < nparts; s0 += 8) {
+    float4 t0[8], t1[8];
+    uint32_t spins = 0;
+    for (;;) {
+      bool ok = true;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (s0 + j < nparts) {
+          const float2* p = parts + (static_cast<long long>(s0 + j) * B + b) * rows + i4;
+          t0[j] = ldp2(p), t1[j] = ldp2(p + 2);
+        } else {
+          t0[j] = t1[j] = make_float4(0.f, __int_as_float(pstamp), 0.f, __int_as_float(pstamp));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        ok = ok && __float_as_int(t0[j].y) == pstamp && __float_as_int(t0[j].w) == pstamp && __float_as_int(t1[j].y) == pstamp &&
+             __float_as_int(t1[j].w) == pstamp;
+      if (ok) break;
+      tc_spin_check(spins, "split-K slices");
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0] += t0[j].x, acc[1] += t0[j].z, acc[2] += t1[j].x, acc[3] += t1[j].z;
+  }
+}
+
 constexpr int kPhQ = 0, kPhO = 1, kPhG = 2, kPhD = 3;
+
+constexpr int kAttWarps = 4;   // warps that walk KV pages in the attention phase
 
 // shared-memory misc block (after the ring and the union region)
 struct TcMisc {
@@ -86,7 +153,7 @@ struct TcMisc {
   uint64_t bop_bar;
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
-  AttnSync attn;
+  uint64_t att_bar[kAttWarps];
   uint32_t tmem_slot;
   int go;                 // steps released to the stream / MMA warps so far, -1 = stop
   int pos[kTcMaxBatch];   // this step's seq_lens snapshot
@@ -95,19 +162,20 @@ struct TcMisc {
   float tile_max[2][4][kTcMaxBatch];
   float rstd[8];
   int sel[8];
+  int nchunks[4];         // B-operand chunks of this CTA's items per split phase
+  int ckb[4][16];         // k-block staged in chunk c (qkv / down: k-block of the input; o_proj: head)
   TcPlan plan;
 };
 
-// Attention staging (fp32 CUDA-core path): one 64-token K page + V page, the group's queries, running softmax state.
+// Attention staging: four warps each own a K page + V page buffer (SWIZZLE_128B, filled by TMA) and walk the pages
+// of this CTA's split independently; per-warp partial outputs merge through shared memory.
 struct TcAttnSmem {
-  __nv_bfloat16 k[64 * 64];
-  __nv_bfloat16 v[64 * 64];
-  float q[8][64];
-  float s[8][64];
-  float ml[8][2];
-  float corr[8];
-  float red[4][8][64];
-  float knew[64], vnew[64];
+  __nv_bfloat16 k[kAttWarps][64 * 64];   // 8 KB each => 1024-byte aligned inside the 1024-aligned union region
+  __nv_bfloat16 v[kAttWarps][64 * 64];
+  float o[kAttWarps][8][64];             // per-warp unnormalised outputs [head][dim]
+  float ml[kAttWarps][8][2];
+  float q[8][64];                        // this group's queries after bias + RoPE (fp32)
+  float knew[64], vnew[64];              // the new token's K / V row
 };
 
 // ------------------------------------------------------------------------------------------ the kernel
@@ -115,6 +183,11 @@ template <int NT, bool HILO>
 __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_constant__ TcParams P) {
   constexpr int CHUNK = NT * 128;            // bytes of one B-operand k-block
   constexpr int NTOK = HILO ? 8 : NT;        // token slots on the N axis
+  // MMAs into one accumulator tile form a dependent chain (~150 cycles each at N = 16): the four 16-wide k-steps of
+  // a k-block go to NACC independent TMEM tiles instead, summed by the epilogue (fixed order).
+  constexpr int NACC = NT == 16 ? 4 : (NT == 32 ? 2 : 1);
+  constexpr int ACOLS = NACC * NT;           // TMEM columns of one accumulator buffer
+  constexpr int TMEM_COLS = 2 * ACOLS < 32 ? 32 : 2 * ACOLS;
   extern __shared__ uint8_t tc_smem_raw[];
   uint8_t* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
   uint8_t* ring = smem;
@@ -140,19 +213,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       mbar_init(&ms->acc_full[i], 1);
       mbar_init(&ms->acc_empty[i], 4);
     }
-    mbar_init(&ms->attn.bar, 1);
-    ms->attn.uses = 0;
+    for (int i = 0; i < kAttWarps; ++i) mbar_init(&ms->att_bar[i], 1);
     fence_barrier_init();
     ms->go = 1;
   }
   for (int i = tid; i < static_cast<int>(sizeof(TcPlan) / 4); i += kTcThreads)
     reinterpret_cast<int*>(&ms->plan)[i] = reinterpret_cast<const int*>(P.plan + blockIdx.x)[i];
-  if (warp == 9) tmem_alloc(&ms->tmem_slot, 2 * NT < 32 ? 32 : 2 * NT);
+  if (warp == 9) tmem_alloc(&ms->tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ms->tmem_slot;
   const TcPlan& plan = ms->plan;
+  if (tid < 4) {  // chunk tables of the split phases (items in plan order, k-blocks ascending)
+    int c = 0;
+    for (int i = 0; i < plan.n[tid]; ++i)
+      for (int kb = 0; kb < plan.it[tid][i].nkb && c < 16; ++kb, ++c) ms->ckb[tid][c] = plan.it[tid][i].kb0 + kb;
+    ms->nchunks[tid] = c;
+  }
+  __syncthreads();
   const int n_head_tiles = plan.head_t1 - plan.head_t0;
 
   auto wait_go = [&](int step) -> bool {  // stream / MMA warps: released one step at a time (early-exit safety)
@@ -208,14 +287,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         const uint32_t buf = acc_n & 1;
         mbar_wait(&ms->acc_empty[buf], ((acc_n >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t dst = tmem_base + buf * NT;
+        const uint32_t dst = tmem_base + buf * ACOLS;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&ms->full_bar[slot], par);
           tc_fence_after();
           const uint64_t adesc = umma_desc_sw128(smem_u32(ring + static_cast<size_t>(slot) * 16384));
           const uint64_t bdesc = umma_desc_sw128(bop_addr + static_cast<uint32_t>(chunk0 + kb) * CHUNK);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_bf16(dst, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(dst + (k % NACC) * NT, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k >= NACC) ? 1u : 0u);
           umma_commit(&ms->empty_bar[slot]);
           if (++slot == NS) slot = 0, par ^= 1;
         }
@@ -255,12 +335,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
     const unsigned G = gridDim.x;
     unsigned target = 0;
     uint32_t acc_n = 0;
-    TcProf prof{nullptr, 0};
+    TcProf prof{nullptr, 0, false};
+    auto pm = [&](int id) { if (tid == 0 && prof.fine) prof.mark(id); };
     const int n_rep = P.n_heads / P.n_kv;
     const int split_cap = P.split_cap;
     const bool fold_cta = P.fold_in_cta != 0;
+    const int I = P.inter;
     float* xf = reinterpret_cast<float*>(uni + 14 * CHUNK);   // fold_in_cta: fp32 folded rows [B][H] behind the B chunks
+    float* xw = xf + 4096;                                      // ... and the RMSNorm weight row [H] (H <= 1024)
     TcAttnSmem* asmem = reinterpret_cast<TcAttnSmem*>(uni);
+    int fold_no = 0;   // fold_in_cta: folds done in this launch (ping-pong parity + stamp of the residual stream)
 
     // ---- grid barrier; `post` runs on thread 0 between the release and the trailing CTA barrier
     auto grid_sync = [&](auto post) {
@@ -276,24 +360,21 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
             __trap();
           }
         }
-        prof.mark();
+        prof.mark(200);
         post();
       }
       csync();
     };
     auto no_post = [] {};
+    auto stamp_of = [&](int step, int l) { return P.stamp_base + step * (L + 1) + l + 1; };
 
     // ---- B operand by TMA from global bf16 rows (thread 0, after the barrier that published them)
     auto load_bop_split = [&](const CUtensorMap* m, int ph) {   // chunks of the items' own k ranges, item after item
       const int n = plan.n[ph];
       if (n == 0) return;
-      int total = 0;
-      for (int i = 0; i < n; ++i) total += plan.it[ph][i].nkb;
       fence_proxy_async_all();
-      mbar_arrive_expect_tx(&ms->bop_bar, static_cast<uint32_t>(total) * CHUNK);
-      int c = 0;
-      for (int i = 0; i < n; ++i)
-        for (int kb = 0; kb < plan.it[ph][i].nkb; ++kb, ++c) tma_load_2d(uni + c * CHUNK, m, (plan.it[ph][i].kb0 + kb) * 64, 0, &ms->bop_bar);
+      mbar_arrive_expect_tx(&ms->bop_bar, static_cast<uint32_t>(ms->nchunks[ph]) * CHUNK);
+      for (int c = 0; c < ms->nchunks[ph]; ++c) tma_load_2d(uni + c * CHUNK, m, ms->ckb[ph][c] * 64, 0, &ms->bop_bar);
     };
     auto load_bop_full = [&](const CUtensorMap* m, bool need) {  // all KBH chunks of the hidden-sized K
       if (!need) return;
@@ -313,13 +394,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       const uint32_t buf = acc_n & 1;
       mbar_wait(&ms->acc_full[buf], (acc_n >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * NT;
-      if constexpr (NT == 16) {
-        uint32_t r[16];
-        tmem_ld16(taddr, r);
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + buf * ACOLS;
+      if constexpr (NT == 16) {   // 4 sub-accumulators of 16 columns
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 16; ++j)
+          v[j] = (__uint_as_float(r0[j]) + __uint_as_float(r0[16 + j])) + (__uint_as_float(r1[j]) + __uint_as_float(r1[16 + j]));
+      } else if constexpr (NT == 32) {   // 2 sub-accumulators of 32 columns
+        uint32_t r0[32], r1[32];
+        tmem_ld32(taddr, r0);
+        tmem_ld32(taddr + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
       } else {
 #pragma unroll
         for (int c = 0; c < NT / 32; ++c) {
@@ -340,34 +430,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       }
     };
 
-    // ---- epilogue of the split-K phases: raw partial sums, one row per lane, coalesced over the warp
-    auto epi_partials = [&](int ph, float* part, int rows) {
+    // ---- epilogue of the split-K phases: raw partial sums as (value, stamp) pairs, one row per lane
+    auto epi_partials = [&](int ph, float2* part, int rows, int stamp) {
       if (warp >= 4) return;
+      const float sf = __int_as_float(stamp);
       for (int i = 0; i < plan.n[ph]; ++i) {
         const TcItem it = plan.it[ph][i];
         float v[NT];
         acc_take(v);
+        pm(10);
         const int row = it.tile * 128 + warp * 32 + lane;
         if (row < rows) {
-          float* dst = part + (static_cast<long long>(it.slice) * B) * rows + row;
+          float2* dst = part + (static_cast<long long>(it.slice) * B) * rows + row;
 #pragma unroll
           for (int n = 0; n < NTOK; ++n)
-            if (n < B) dst[static_cast<long long>(n) * rows] = v[n];
+            if (n < B) dst[static_cast<long long>(n) * rows] = make_float2(v[n], sf);
         }
       }
     };
 
-    // ---- fold + RMSNorm of ONE token row by its owner CTA -> residual stream (fp32) + normalised bf16 rows
-    auto fold_phase = [&](const float* parts, int nparts, int rows, const float* norm_w) {
+    // ---- batch > 4: fold + RMSNorm of ONE token row by its owner CTA -> residual stream (fp32) + normalised bf16 rows
+    auto fold_phase = [&](const float2* parts, int nparts, int pstamp, int rows, const float* norm_w) {
       const int b = blockIdx.x;
       if (b >= B) return;
       float* hb = P.h + static_cast<long long>(b) * H;
       float ss = 0.f;
-      for (int i = tid; i < H; i += kConsumerThreads) {
-        float v = __ldcg(hb + i);
-        for (int s = 0; s < nparts; ++s) v += __ldcg(parts + (static_cast<long long>(s) * B + b) * rows + i);
-        hb[i] = v;
-        ss += v * v;
+      for (int i4 = tid * 4; i4 < H; i4 += 4 * kConsumerThreads) {
+        float acc[4];
+        tc_fold4(nullptr, 0, parts, nparts, pstamp, rows, B, H, b, i4, acc);
+        const float4 hv = __ldcg(reinterpret_cast<const float4*>(hb + i4));
+        acc[0] += hv.x, acc[1] += hv.y, acc[2] += hv.z, acc[3] += hv.w;
+        *reinterpret_cast<float4*>(hb + i4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        ss += acc[0] * acc[0] + acc[1] * acc[1] + acc[2] * acc[2] + acc[3] * acc[3];
       }
       ss = warp_sum(ss);
       if (lane == 0) ms->red[warp] = ss;
@@ -376,28 +470,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
 #pragma unroll
       for (int w = 0; w < kConsumerWarps; ++w) t += ms->red[w];
       const float sc = rsqrtf(t / static_cast<float>(H) + P.eps);
-      for (int i = tid; i < H; i += kConsumerThreads) {
-        const float xn = __ldg(norm_w + i) * (hb[i] * sc);   // hb[i]: this thread's own store above
+      for (int i4 = tid * 4; i4 < H; i4 += 4 * kConsumerThreads) {
+        const float4 hv = *reinterpret_cast<const float4*>(hb + i4);   // this thread's own stores above
+        const float4 g = __ldg(reinterpret_cast<const float4*>(norm_w + i4));
+        const float xn[4] = {g.x * (hv.x * sc), g.y * (hv.y * sc), g.z * (hv.z * sc), g.w * (hv.w * sc)};
         if constexpr (HILO) {
-          __nv_bfloat16 hi, lo;
-          split_hilo(xn, hi, lo);
-          P.xa[static_cast<long long>(b) * H + i] = hi;
-          P.xa[static_cast<long long>(8 + b) * H + i] = lo;
+          __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split_hilo(xn[j], hi[j], lo[j]);
+          *reinterpret_cast<uint2*>(P.xa + static_cast<long long>(b) * H + i4) =
+              make_uint2(pack2(hi[0], hi[1]), pack2(hi[2], hi[3]));
+          *reinterpret_cast<uint2*>(P.xa + static_cast<long long>(8 + b) * H + i4) =
+              make_uint2(pack2(lo[0], lo[1]), pack2(lo[2], lo[3]));
         } else {
-          P.xa[static_cast<long long>(b) * H + i] = __float2bfloat16(xn);
+          *reinterpret_cast<uint2*>(P.xa + static_cast<long long>(b) * H + i4) =
+              make_uint2(pack_bf16x2(xn[0], xn[1]), pack_bf16x2(xn[2], xn[3]));
         }
       }
     };
 
-    // ---- batch <= 4: fold ALL rows in this CTA (h + slices, slice order), normalise, stage `nchunk` B chunks
-    //      (k-blocks listed per item for split phases, or all of them) -- no fold phase, no barrier
-    auto fold_stage = [&](const float* parts, int nparts, int rows, const float* norm_w, int ph /* -1: all k-blocks */) {
-      for (int e = tid; e < B * H; e += kConsumerThreads) {
-        const int b = e / H, i = e - b * H;
-        float v = __ldcg(P.h + e);
-        for (int s = 0; s < nparts; ++s) v += __ldcg(parts + (static_cast<long long>(s) * B + b) * rows + i);
-        xf[e] = v;
+    // ---- batch <= 4: fold ALL rows in this CTA (residual pairs + slices, slice order), normalise, stage the B chunks
+    //      of phase `ph` (-1: every k-block).  The designated CTA publishes the folded stream for the next fold.
+    auto fold_stage = [&](const float2* parts, int nparts, int pstamp, int rows, const float* norm_w, int ph, bool writer) {
+      const float2* hsrc = P.h2 + static_cast<long long>(fold_no & 1) * B * H;
+      const int hstamp = P.hstamp_base + fold_no;
+      const int nq = H >> 2;
+      pm(1);
+      for (int q = tid; q < B * nq; q += kConsumerThreads) {
+        const int b = q / nq, i4 = (q - b * nq) * 4;
+        float acc[4];
+        const float4 nw = __ldg(reinterpret_cast<const float4*>(norm_w + i4));   // in flight together with the slices
+        tc_fold4(hsrc, hstamp, parts, nparts, pstamp, rows, B, H, b, i4, acc);
+        *reinterpret_cast<float4*>(xf + b * H + i4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (b == 0) *reinterpret_cast<float4*>(xw + i4) = nw;
       }
+      pm(2);
       csync();
       if (warp < B) {  // warp b: sum of squares of row b
         float ss = 0.f;
@@ -406,37 +513,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         if (lane == 0) ms->rstd[warp] = rsqrtf(ss / static_cast<float>(H) + P.eps);
       }
       csync();
-      auto stage_chunk = [&](int chunk, int kb) {
-        uint8_t* cb = uni + chunk * CHUNK;
-        for (int e = tid; e < B * 64; e += kConsumerThreads) {
-          const int b = e >> 6, k = e & 63;
-          const int i = kb * 64 + k;
-          const float xn = __ldg(norm_w + i) * (xf[b * H + i] * ms->rstd[b]);
-          __nv_bfloat16 hi, lo;
-          split_hilo(xn, hi, lo);
-          *chunk_elem(cb, b, k) = hi;
-          *chunk_elem(cb, 8 + b, k) = lo;
-        }
-      };
-      if (ph < 0) {
-        for (int kb = 0; kb < KBH; ++kb) stage_chunk(kb, kb);
-      } else {
-        int c = 0;
-        for (int i = 0; i < plan.n[ph]; ++i)
-          for (int kb = 0; kb < plan.it[ph][i].nkb; ++kb, ++c) stage_chunk(c, plan.it[ph][i].kb0 + kb);
+      const int nch = ph < 0 ? KBH : ms->nchunks[ph];
+      const int per = B * 64;
+      for (int e = tid; e < nch * per; e += kConsumerThreads) {
+        const int c = e / per, r = e - c * per, b = r >> 6, k = r & 63;
+        const int i = (ph < 0 ? c : ms->ckb[ph][c]) * 64 + k;
+        const float xn = xw[i] * (xf[b * H + i] * ms->rstd[b]);
+        __nv_bfloat16 hi, lo;
+        split_hilo(xn, hi, lo);
+        uint8_t* cb = uni + c * CHUNK;
+        *chunk_elem(cb, b, k) = hi;
+        *chunk_elem(cb, 8 + b, k) = lo;
       }
+      pm(4);
       bop_ready();
-    };
-    auto write_back_h = [&] {  // the designated CTA publishes the folded residual stream (after the phase's barrier)
-      for (int e = tid; e < B * H; e += kConsumerThreads) P.h[e] = xf[e];
-      csync();  // xf lies in the union region: nobody may reuse it before every thread has read its part
+      pm(5);
+      if (writer) {
+        float2* hdst = P.h2 + static_cast<long long>((fold_no + 1) & 1) * B * H;
+        const float sf = __int_as_float(hstamp + 1);
+        for (int q = tid; q < B * nq; q += kConsumerThreads) {
+          const float4 v = *reinterpret_cast<const float4*>(xf + q * 4);
+          float4* d = reinterpret_cast<float4*>(hdst + q * 4);
+          d[0] = make_float4(v.x, sf, v.y, sf);
+          d[1] = make_float4(v.z, sf, v.w, sf);
+        }
+      }
+      ++fold_no;
     };
 
     // ---- attention item of this CTA: (sequence, kv head, split)
     const int per_b = P.n_kv * split_cap;
     const int my_b = blockIdx.x / per_b, my_kvh = (blockIdx.x % per_b) / split_cap, my_split = blockIdx.x % split_cap;
 
-    auto attention_phase = [&](int l) {
+    uint32_t att_par = 0;   // parity of this warp's page barrier (warps 0..3)
+    const CUtensorMap* kvmap = &P.kvmap;
+    auto attention_phase = [&](int l, int stamp) {
       if (my_b >= B) return;
       const int pos = ms->pos[my_b];
       const SplitGeom geo = split_geom(pos, P.kv.max_ctx, split_cap);
@@ -444,10 +555,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       const int b = my_b, kvh = my_kvh;
       const int p0 = my_split * geo.pps, p1 = min(p0 + geo.pps, geo.npages);
       const bool appends = pos < P.kv.max_ctx && (pos >> 6) >= p0 && (pos >> 6) < p1;
-      // prologue: fold the qkv slices (slice order) + bias, RoPE; q of the group -> shared; new K/V row -> page
+      const int krow0 = l * 2 * P.kv.num_pages * P.kv.n_kv_heads * 64;
+      const int vrow0 = krow0 + P.kv.num_pages * P.kv.n_kv_heads * 64;
+      auto issue_page = [&](int pg) {   // lane 0 of an attention warp: K and V page of (sequence, kv head) -> this warp's buffers
+        const int page = __ldcg(P.kv.page_table + b * P.kv.max_pages_per_seq + pg);
+        fence_proxy_async_all();
+        mbar_arrive_expect_tx(&ms->att_bar[warp], 2 * 8192);
+        tma_load_2d(asmem->k[warp], kvmap, 0, krow0 + (page * P.kv.n_kv_heads + kvh) * 64, &ms->att_bar[warp]);
+        tma_load_2d(asmem->v[warp], kvmap, 0, vrow0 + (page * P.kv.n_kv_heads + kvh) * 64, &ms->att_bar[warp]);
+      };
+      // the pages do not depend on this layer's projections (the new row is patched in below): fetch the first round now
+      csync();   // the union region is ours (previous phase of this CTA is through with it)
+      if (warp < kAttWarps && lane == 0 && p0 + warp < p1) issue_page(p0 + warp);
+      pm(21);
+      // prologue: fold the qkv slices (slice order) + bias, RoPE; q of the group -> shared; new K/V row
       const float* bias = P.bqkv[l];
       const int QN = P.qkv_n;
-      const float* pq = P.part_q + static_cast<long long>(b) * QN;
+      const float2* pq = P.pq2 + static_cast<long long>(b) * QN;
       const long long sstride = static_cast<long long>(B) * QN;
       for (int idx = tid; idx < n_rep * 32 + 64; idx += kConsumerThreads) {
         int row0;
@@ -457,168 +581,249 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         else if (which == 1) row0 = (P.n_heads + kvh) * 64 + 2 * i;
         else row0 = (P.n_heads + P.n_kv + kvh) * 64 + 2 * i;
         if (which != 0 && !appends) continue;
+        const float2 bia = __ldg(reinterpret_cast<const float2*>(bias + row0));
+        float sn = 0.f, cs = 1.f;
+        if (which != 2) sincosf(static_cast<float>(pos) * __ldg(P.inv_freq + i), &sn, &cs);
         float2 a = make_float2(0.f, 0.f);
-        for (int s = 0; s < P.sq; ++s) {
-          const float2 t = __ldcg(reinterpret_cast<const float2*>(pq + s * sstride + row0));
-          a.x += t.x, a.y += t.y;
+        for (int s0 = 0; s0 < P.sq; s0 += 8) {
+          float4 t[8];
+          uint32_t spins = 0;
+          for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              t[j] = (s0 + j < P.sq) ? ldp2(pq + (s0 + j) * sstride + row0) : make_float4(0.f, __int_as_float(stamp), 0.f, __int_as_float(stamp));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) ok = ok && __float_as_int(t[j].y) == stamp && __float_as_int(t[j].w) == stamp;
+            if (ok) break;
+            tc_spin_check(spins, "qkv slices");
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a.x += t[j].x, a.y += t[j].z;
         }
-        a.x += __ldg(bias + row0), a.y += __ldg(bias + row0 + 1);
+        a.x += bia.x, a.y += bia.y;
         if (which == 2) {
           asmem->vnew[2 * i] = a.x, asmem->vnew[2 * i + 1] = a.y;
         } else {
-          float sn, cs;
-          sincosf(static_cast<float>(pos) * __ldg(P.inv_freq + i), &sn, &cs);
           const float lo = a.x * cs - a.y * sn, hi = a.y * cs + a.x * sn;   // rows (2i, 2i+1) = dims (i, i + 32)
           if (which == 0) asmem->q[idx >> 5][i] = lo, asmem->q[idx >> 5][i + 32] = hi;
           else asmem->knew[i] = lo, asmem->knew[i + 32] = hi;
         }
       }
-      if (tid < 8) asmem->ml[tid][0] = -INFINITY, asmem->ml[tid][1] = 0.f;
+      pm(22);
       csync();
-      if (appends && tid < 64) {  // the new token's K/V row joins the cache (bf16) for the steps to come
+      if (appends && tid >= 128 && tid < 192) {  // the new token's K/V row joins the cache (bf16) for the steps to come
+        const int d = tid - 128;
         const int page = __ldcg(P.kv.page_table + b * P.kv.max_pages_per_seq + (pos >> 6));
-        P.kv.page_ptr(l, 0, page, kvh)[(pos & 63) * 64 + tid] = __float2bfloat16(asmem->knew[tid]);
-        P.kv.page_ptr(l, 1, page, kvh)[(pos & 63) * 64 + tid] = __float2bfloat16(asmem->vnew[tid]);
+        P.kv.page_ptr(l, 0, page, kvh)[(pos & 63) * 64 + d] = __float2bfloat16(asmem->knew[d]);
+        P.kv.page_ptr(l, 1, page, kvh)[(pos & 63) * 64 + d] = __float2bfloat16(asmem->vnew[d]);
       }
-      float acc[8];
+      if (warp < kAttWarps) {
+        const int g = lane >> 2, t = lane & 3, lrow = lane & 7, lmat = lane >> 3;
+        // query fragments: row g = head g of the group (rows >= n_rep and rows 8..15 are zero); scale * log2(e) folded in
+        uint32_t qa[4][4];
+        {
+          const float* qp = asmem->q[min(g, n_rep - 1)];
+          const float sc = (g < n_rep) ? P.scale_log2 : 0.f;
 #pragma unroll
-      for (int h = 0; h < 8; ++h) acc[h] = 0.f;
-      AttnSync* sy = &ms->attn;
-      for (int pg = p0; pg < p1; ++pg) {
-        const uint32_t parity = sy->uses & 1;
-        csync();  // previous page fully consumed; everyone has read `uses`
-        if (tid == 0) {
-          const int page = __ldcg(P.kv.page_table + b * P.kv.max_pages_per_seq + pg);
-          fence_proxy_async_all();
-          mbar_arrive_expect_tx(&sy->bar, 2 * 8192);
-          bulk_g2s(asmem->k, P.kv.page_ptr(l, 0, page, kvh), 8192, &sy->bar);
-          bulk_g2s(asmem->v, P.kv.page_ptr(l, 1, page, kvh), 8192, &sy->bar);
-          sy->uses += 1;
-        }
-        mbar_wait(&sy->bar, parity);
-        if (appends && pg == (pos >> 6)) {  // patch the staged page with the new row (the copy may predate our store)
-          if (tid < 64) {
-            asmem->k[(pos & 63) * 64 + tid] = __float2bfloat16(asmem->knew[tid]);
-            asmem->v[(pos & 63) * 64 + tid] = __float2bfloat16(asmem->vnew[tid]);
-          }
-          csync();
-        }
-        {  // scores: thread = (token, quarter of the head dim)
-          const int tok = tid >> 2, part = tid & 3;
-          const uint4* kr = reinterpret_cast<const uint4*>(asmem->k + tok * 64 + part * 16);
-          float kf[16];
-          {
-            float t[8];
-            bf16x8_to_f32(kr[0], t);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) kf[j] = t[j];
-            bf16x8_to_f32(kr[1], t);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) kf[8 + j] = t[j];
-          }
-          const bool valid = (pg * 64 + tok) < geo.n_ctx;
-          for (int h = 0; h < n_rep; ++h) {
-            float d = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) d += kf[j] * asmem->q[h][part * 16 + j];
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            d += __shfl_xor_sync(0xffffffffu, d, 2);
-            if (part == 0) asmem->s[h][tok] = valid ? d * P.scale_log2 : -INFINITY;
+          for (int j = 0; j < 4; ++j) {
+            const float2 a0 = *reinterpret_cast<const float2*>(qp + 16 * j + 2 * t);
+            const float2 a2 = *reinterpret_cast<const float2*>(qp + 16 * j + 8 + 2 * t);
+            qa[j][0] = pack_bf16x2(a0.x * sc, a0.y * sc);
+            qa[j][1] = 0u;
+            qa[j][2] = pack_bf16x2(a2.x * sc, a2.y * sc);
+            qa[j][3] = 0u;
           }
         }
-        csync();
-        if (warp < n_rep) {  // online softmax update of head `warp`
-          const float s0 = asmem->s[warp][lane], s1 = asmem->s[warp][lane + 32];
-          const float m_old = asmem->ml[warp][0];
-          const float m_new = fmaxf(m_old, warp_max(fmaxf(s0, s1)));  // every page of a live split has a valid token
-          const float p0v = exp2f(s0 - m_new), p1v = exp2f(s1 - m_new);
-          const float lsum = warp_sum(p0v + p1v);
-          asmem->s[warp][lane] = p0v;
-          asmem->s[warp][lane + 32] = p1v;
-          if (lane == 0) {
-            const float c = exp2f(m_old - m_new);  // 0 on the first page (m_old = -inf)
-            asmem->corr[warp] = c;
-            asmem->ml[warp][0] = m_new;
-            asmem->ml[warp][1] = asmem->ml[warp][1] * c + lsum;
+        float o[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+        float m0 = -INFINITY, l0 = 0.f;
+        const uint32_t kbase = smem_u32(asmem->k[warp]), vbase = smem_u32(asmem->v[warp]);
+        for (int pg = p0 + warp; pg < p1; pg += kAttWarps) {
+          mbar_wait(&ms->att_bar[warp], att_par);
+          att_par ^= 1;
+          if (warp == 0) pm(23);
+          if (appends && pg == (pos >> 6)) {  // patch the staged page with the new row (the copy may predate our store)
+            const int r = pos & 63;
+            uint8_t* kb8 = reinterpret_cast<uint8_t*>(asmem->k[warp]);
+            uint8_t* vb8 = reinterpret_cast<uint8_t*>(asmem->v[warp]);
+            *reinterpret_cast<uint32_t*>(chunk_elem(kb8, r, 2 * lane)) = pack_bf16x2(asmem->knew[2 * lane], asmem->knew[2 * lane + 1]);
+            *reinterpret_cast<uint32_t*>(chunk_elem(vb8, r, 2 * lane)) = pack_bf16x2(asmem->vnew[2 * lane], asmem->vnew[2 * lane + 1]);
+            __syncwarp();
           }
-        }
-        csync();
-        {  // P.V : thread = (dim, token group of 16), accumulators carried across pages
-          const int d = tid & 63, g = tid >> 6;
+          float sc[8][4];
 #pragma unroll
-          for (int h = 0; h < 8; ++h)
-            if (h < n_rep) acc[h] *= asmem->corr[h];
-          for (int t = g * 16; t < g * 16 + 16; ++t) {
-            const float v = __bfloat162float(asmem->v[t * 64 + d]);
+          for (int n = 0; n < 8; ++n) {
+            sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+            const int row = 8 * n + lrow;
 #pragma unroll
-            for (int h = 0; h < 8; ++h)
-              if (h < n_rep) acc[h] += asmem->s[h][t] * v;
+            for (int half = 0; half < 2; ++half) {
+              uint32_t kb[4];
+              ldmatrix_x4(kb, kbase + row * 128 + (((4 * half + lmat) ^ lrow) << 4));
+              mma_bf16_16816(sc[n], qa[2 * half], kb[0], kb[1]);
+              mma_bf16_16816(sc[n], qa[2 * half + 1], kb[2], kb[3]);
+            }
           }
-        }
-      }
-      {
-        const int d = tid & 63, g = tid >> 6;
+          const int k0 = pg * 64;
+          if (k0 + 64 > geo.n_ctx) {
 #pragma unroll
-        for (int h = 0; h < 8; ++h)
-          if (h < n_rep) asmem->red[g][h][d] = acc[h];
+            for (int n = 0; n < 8; ++n) {
+              const int kv0 = k0 + 8 * n + 2 * t;
+              if (kv0 >= geo.n_ctx) sc[n][0] = -INFINITY;
+              if (kv0 + 1 >= geo.n_ctx) sc[n][1] = -INFINITY;
+            }
+          }
+          float mx = -INFINITY;
+#pragma unroll
+          for (int n = 0; n < 8; ++n) mx = fmaxf(mx, fmaxf(sc[n][0], sc[n][1]));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1)), mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          const float mn = fmaxf(m0, mx);  // the first token of every page walked is valid -> finite
+          const float c = exp2f(m0 - mn);
+          m0 = mn;
+          l0 *= c;
+#pragma unroll
+          for (int n = 0; n < 8; ++n) o[n][0] *= c, o[n][1] *= c;
+          uint32_t pa[4][4];
+#pragma unroll
+          for (int n = 0; n < 8; ++n) {
+            const float p0v = exp2f(sc[n][0] - mn), p1v = exp2f(sc[n][1] - mn);
+            l0 += p0v + p1v;
+            pa[n >> 1][(n & 1) * 2 + 0] = pack_bf16x2(p0v, p1v);
+            pa[n >> 1][(n & 1) * 2 + 1] = 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int row = 16 * j + 8 * (lmat & 1) + lrow;
+#pragma unroll
+            for (int nd = 0; nd < 8; nd += 2) {
+              uint32_t vb[4];
+              ldmatrix_x4_trans(vb, vbase + row * 128 + (((nd + (lmat >> 1)) ^ lrow) << 4));
+              mma_bf16_16816(o[nd], pa[j], vb[0], vb[1]);
+              mma_bf16_16816(o[nd + 1], pa[j], vb[2], vb[3]);
+            }
+          }
+          __syncwarp();  // all lanes are done with the buffers before lane 0 refills them
+          if (lane == 0 && pg + kAttWarps < p1) issue_page(pg + kAttWarps);
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1), l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        if (g < n_rep) {
+#pragma unroll
+          for (int n = 0; n < 8; ++n) *reinterpret_cast<float2*>(&asmem->o[warp][g][8 * n + 2 * t]) = make_float2(o[n][0], o[n][1]);
+          if (t == 0) asmem->ml[warp][g][0] = m0, asmem->ml[warp][g][1] = l0;
+        }
       }
       csync();
+      const float sf = __int_as_float(stamp);
       for (int i = tid; i < n_rep * 64; i += kConsumerThreads) {
         const int h = i >> 6, d = i & 63;
-        const float o = asmem->red[0][h][d] + asmem->red[1][h][d] + asmem->red[2][h][d] + asmem->red[3][h][d];
-        const long long hh = static_cast<long long>(b) * P.n_heads + kvh * n_rep + h;
-        P.att_o[(hh * P.max_splits + my_split) * 64 + d] = o;
-        if (d == 0) {
-          P.att_ml[(hh * P.max_splits + my_split) * 2 + 0] = asmem->ml[h][0];
-          P.att_ml[(hh * P.max_splits + my_split) * 2 + 1] = asmem->ml[h][1];
+        float M = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kAttWarps; ++w) M = fmaxf(M, asmem->ml[w][h][0]);
+        float Ls = 0.f, O = 0.f;
+#pragma unroll
+        for (int w = 0; w < kAttWarps; ++w) {
+          const float wgt = exp2f(asmem->ml[w][h][0] - M);   // 0 for a warp that walked no page (m = -inf, l = 0)
+          Ls += wgt * asmem->ml[w][h][1];
+          O += wgt * asmem->o[w][h][d];
         }
+        const long long hh = static_cast<long long>(b) * P.n_heads + kvh * n_rep + h;
+        P.ao2[(hh * P.max_splits + my_split) * 64 + d] = make_float2(O, sf);
+        if (d == 0) *reinterpret_cast<float4*>(P.aml2 + (hh * P.max_splits + my_split) * 2) = make_float4(M, sf, Ls, sf);
       }
+      pm(25);
+      csync();   // the union region is free again
     };
 
     // ---- o_proj input: merge the split-KV partials of the heads this CTA's items need, straight into B chunks
-    auto stage_attn = [&] {
-      int c = 0;
-      for (int i = 0; i < plan.n[kPhO]; ++i)
-        for (int kb = 0; kb < plan.it[kPhO][i].nkb; ++kb, ++c) {
-          const int head = plan.it[kPhO][i].kb0 + kb;
-          uint8_t* cb = uni + c * CHUNK;
-          for (int e = tid; e < B * 64; e += kConsumerThreads) {
-            const int b = e >> 6, d = e & 63;
-            const SplitGeom g = split_geom(ms->pos[b], P.kv.max_ctx, split_cap);
-            const long long hh = static_cast<long long>(b) * P.n_heads + head;
-            const float2* ml = reinterpret_cast<const float2*>(P.att_ml) + hh * P.max_splits;
-            const float* po = P.att_o + hh * P.max_splits * 64 + d;
-            float M = -INFINITY;
-            for (int s = 0; s < g.nsplit; ++s) M = fmaxf(M, __ldcg(ml + s).x);
-            float Ls = 0.f, O = 0.f;
-            for (int s = 0; s < g.nsplit; ++s) {
-              const float2 t = __ldcg(ml + s);
-              const float wgt = exp2f(t.x - M);
-              Ls += wgt * t.y;
-              O += wgt * __ldcg(po + s * 64);
-            }
-            const float val = O / Ls;
-            if constexpr (HILO) {
-              __nv_bfloat16 hi, lo;
-              split_hilo(val, hi, lo);
-              *chunk_elem(cb, b, d) = hi;
-              *chunk_elem(cb, 8 + b, d) = lo;
-            } else {
-              *chunk_elem(cb, b, d) = __float2bfloat16(val);
-            }
-          }
+    auto stage_attn = [&](int stamp) {
+      const int nch = ms->nchunks[kPhO];
+      const int per = B * 64;
+      for (int e = tid; e < nch * per; e += kConsumerThreads) {
+        const int c = e / per, r = e - c * per, b = r >> 6, d = r & 63;
+        const int head = ms->ckb[kPhO][c];
+        const SplitGeom g = split_geom(ms->pos[b], P.kv.max_ctx, split_cap);
+        const long long hh = static_cast<long long>(b) * P.n_heads + head;
+        const float2* ml = P.aml2 + hh * P.max_splits * 2;
+        const float2* po = P.ao2 + hh * P.max_splits * 64 + d;
+        float4 mv[8];
+        float2 ov[8];
+        uint32_t spins = 0;
+        for (;;) {   // split_cap <= 8: one batch of loads
+          bool ok = true;
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            if (s < g.nsplit) mv[s] = ldp2(ml + 2 * s), ov[s] = ldp1(po + s * 64);
+#pragma unroll
+          for (int s = 0; s < 8; ++s)
+            if (s < g.nsplit)
+              ok = ok && __float_as_int(mv[s].y) == stamp && __float_as_int(mv[s].w) == stamp && __float_as_int(ov[s].y) == stamp;
+          if (ok) break;
+          tc_spin_check(spins, "attention partials");
         }
+        float M = -INFINITY;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < g.nsplit) M = fmaxf(M, mv[s].x);
+        float Ls = 0.f, O = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; ++s)
+          if (s < g.nsplit) {
+            const float wgt = exp2f(mv[s].x - M);
+            Ls += wgt * mv[s].z;
+            O += wgt * ov[s].x;
+          }
+        const float val = O / Ls;
+        uint8_t* cb = uni + c * CHUNK;
+        if constexpr (HILO) {
+          __nv_bfloat16 hi, lo;
+          split_hilo(val, hi, lo);
+          *chunk_elem(cb, b, d) = hi;
+          *chunk_elem(cb, 8 + b, d) = lo;
+        } else {
+          *chunk_elem(cb, b, d) = __float2bfloat16(val);
+        }
+      }
+      pm(31);
       bop_ready();
+      pm(32);
+    };
+
+    // ---- batch <= 4: down_proj input from the (value, stamp) SwiGLU outputs, two elements per thread
+    auto stage_act = [&](int stamp) {
+      const int nch = ms->nchunks[kPhD];
+      const int per = B * 32;
+      for (int e = tid; e < nch * per; e += kConsumerThreads) {
+        const int c = e / per, r = e - c * per, b = r >> 5, k = (r & 31) * 2;
+        const float2* p = P.act2 + static_cast<long long>(b) * I + ms->ckb[kPhD][c] * 64 + k;
+        float4 t;
+        uint32_t spins = 0;
+        for (;;) {
+          t = ldp2(p);
+          if (__float_as_int(t.y) == stamp && __float_as_int(t.w) == stamp) break;
+          tc_spin_check(spins, "SwiGLU outputs");
+        }
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_hilo(t.x, h0, l0);
+        split_hilo(t.z, h1, l1);
+        uint8_t* cb = uni + c * CHUNK;
+        *reinterpret_cast<uint32_t*>(chunk_elem(cb, b, k)) = pack2(h0, h1);
+        *reinterpret_cast<uint32_t*>(chunk_elem(cb, 8 + b, k)) = pack2(l0, l1);
+      }
+      pm(41);
+      bop_ready();
+      pm(42);
     };
 
     // ---- gate/up epilogue: rows (2j, 2j+1) = (gate_j, up_j) on adjacent lanes -> act[b][j] = silu(gate) * up
-    auto epi_swiglu = [&] {
+    auto epi_swiglu = [&](int stamp) {
       if (warp >= 4) return;
-      const int I = P.inter;
+      const float sf = __int_as_float(stamp);
       for (int i = 0; i < plan.n[kPhG]; ++i) {
         const TcItem it = plan.it[kPhG][i];
         float v[NT];
         acc_take(v);
+        pm(50);
         const int row = it.tile * 128 + warp * 32 + lane;
         const int j = row >> 1;
 #pragma unroll
@@ -626,7 +831,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
           const float up = __shfl_down_sync(0xffffffffu, v[n], 1);
           if (n < B && !(lane & 1) && j < I) {
             const float a = silu(v[n]) * up;
-            if constexpr (HILO) {
+            if (fold_cta) {
+              P.act2[static_cast<long long>(n) * I + j] = make_float2(a, sf);
+            } else if constexpr (HILO) {
               __nv_bfloat16 hi, lo;
               split_hilo(a, hi, lo);
               P.act[static_cast<long long>(n) * I + j] = hi;
@@ -652,14 +859,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         const int row = tile * 128 + warp * 32 + lane;
         const bool ok = row < V;
         float (*tm)[kTcMaxBatch] = ms->tile_max[t & 1];
+        float pv[NTOK];
 #pragma unroll
         for (int n = 0; n < NTOK; ++n) {
-          if (n < B) {   // uniform across the warp
+          pv[n] = -INFINITY;
+          if (n < B) {
             if (ok) P.logits[static_cast<long long>(n) * V + row] = v[n];
-            float pv = (!ok || (ms->mask_eos[n] && row == eos)) ? -INFINITY : v[n] * inv_t;
-            pv = warp_max(pv);
-            if (lane == 0) tm[warp][n] = pv;
+            if (ok && !(ms->mask_eos[n] && row == eos)) pv[n] = v[n] * inv_t;
           }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {   // all columns advance together: independent shuffles pipeline
+#pragma unroll
+          for (int n = 0; n < NTOK; ++n) pv[n] = fmaxf(pv[n], __shfl_xor_sync(0xffffffffu, pv[n], off));
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int n = 0; n < NTOK; ++n)
+            if (n < B) tm[warp][n] = pv[n];
         }
         bar_epi();
         if (tid < B) P.tmax[static_cast<long long>(tid) * P.ntiles + tile] = fmaxf(fmaxf(tm[0][tid], tm[1][tid]), fmaxf(tm[2][tid], tm[3][tid]));
@@ -736,7 +953,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       }
       csync();
       const int ncand = min(min(ms->sel[0], key_cap), 256 * kTopKeep);   // beyond: thousands of exact ties at the threshold
-      // pass 2: write the candidates at their deterministic offsets (layout sample_stage2_seq expects: [b * ncand + i])
+      // pass 2: write the candidates at their deterministic offsets
       constexpr long long kCandPitch = 256 * kTopKeep;   // row pitch of the candidate arrays (sampler_scratch_floats)
       float* cv = P.samp.cand_val + static_cast<long long>(b) * kCandPitch;
       int32_t* ci = P.samp.cand_idx + static_cast<long long>(b) * kCandPitch;
@@ -761,12 +978,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       }
       csync();
       sample_stage2_seq(P.samp, b, ncand, keys, scratch, win, s_tok, csync, NoMark(), kCandPitch);
+      if (fold_cta) {  // the next token's embedding becomes the residual stream of the next step's first fold
+        csync();
+        float2* hdst = P.h2 + (static_cast<long long>(fold_no & 1) * B + b) * H;
+        const float sf = __int_as_float(P.hstamp_base + fold_no);
+        for (int i = tid; i < H; i += kConsumerThreads) hdst[i] = make_float2(P.h[static_cast<long long>(b) * H + i], sf);
+      }
     };
 
     // =============================================================== the decode loop
+    if (fold_cta) {  // hand the prefill's residual rows to the stamped ping-pong buffer (stamp of "fold -1")
+      if (static_cast<int>(blockIdx.x) < B) {
+        const int b = blockIdx.x;
+        const float sf = __int_as_float(P.hstamp_base);
+        for (int i = tid; i < H; i += kConsumerThreads)
+          P.h2[static_cast<long long>(b) * H + i] = make_float2(__ldcg(P.h + static_cast<long long>(b) * H + i), sf);
+      }
+      grid_sync(no_post);
+    }
     for (int step = 0; step < P.n_steps; ++step) {
-      if (P.prof && tid == 0 && step == P.prof_step && blockIdx.x == 0) {
-        prof.buf = P.prof;
+      if (P.prof && tid == 0 && step == P.prof_step && blockIdx.x < 2) {   // CTA 0 (split phases + attention), CTA 1 (gate/up)
+        prof.buf = P.prof + 1024 * blockIdx.x;
         prof.n = 0;
         prof.mark();
       } else {
@@ -777,49 +1009,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         ms->mask_eos[tid] = __ldcg(P.samp.n_generated + tid) < P.samp.sp.min_new_tokens ? 1 : 0;
       }
       csync();
-      if (!fold_cta) {
-        fold_phase(nullptr, 0, H, L > 0 ? P.ln1[0] : P.final_norm);
+      if (fold_cta) {
+        // ---------------- batch <= 4: no grid barrier inside the layers, every hand-off is polled
+        for (int l = 0; l < L; ++l) {
+          const int st = stamp_of(step, l);
+          prof.fine = prof.buf != nullptr && l == 2;
+          if (plan.n[kPhQ] > 0) fold_stage(P.pd2, l > 0 ? P.sd : 0, stamp_of(step, l - 1), H, P.ln1[l], kPhQ, plan.fold_q != 0);
+          else ++fold_no;
+          epi_partials(kPhQ, P.pq2, P.qkv_n, st);
+          if (tid == 0) prof.mark(100);
+          attention_phase(l, st);
+          if (tid == 0) prof.mark(101);
+          if (plan.n[kPhO] > 0) stage_attn(st);
+          epi_partials(kPhO, P.po2, H, st);
+          if (tid == 0) prof.mark(102);
+          if (plan.n[kPhG] > 0) fold_stage(P.po2, P.so, st, H, P.ln2[l], -1, plan.fold_g != 0);
+          else ++fold_no;
+          epi_swiglu(st);
+          if (tid == 0) prof.mark(103);
+          if (plan.n[kPhD] > 0) stage_act(st);
+          epi_partials(kPhD, P.pd2, H, st);
+          if (tid == 0) prof.mark(104);
+        }
+        if (n_head_tiles > 0) fold_stage(P.pd2, L > 0 ? P.sd : 0, stamp_of(step, L - 1), H, P.final_norm, -1, false);
+        else ++fold_no;
+      } else {
+        // ---------------- batch > 4: token-owner fold phases feed the consumers by TMA (3 barriers per layer)
+        fold_phase(nullptr, 0, 0, H, L > 0 ? P.ln1[0] : P.final_norm);
         if (L > 0) grid_sync([&] { load_bop_split(xmap, kPhQ); });
         else grid_sync([&] { load_bop_full(xmap, n_head_tiles > 0); });
-      }
-      for (int l = 0; l < L; ++l) {
-        // ---- qkv
-        if (fold_cta && plan.n[kPhQ] > 0) fold_stage(l > 0 ? P.part_d : nullptr, l > 0 ? P.sd : 0, H, P.ln1[l], kPhQ);
-        epi_partials(kPhQ, P.part_q, P.qkv_n);
-        grid_sync(no_post);
-        if (fold_cta && plan.fold_q && l > 0) write_back_h();
-        // ---- attention
-        attention_phase(l);
-        grid_sync(no_post);
-        // ---- o_proj
-        if (plan.n[kPhO] > 0) stage_attn();
-        epi_partials(kPhO, P.part_o, H);
-        if (!fold_cta) {
-          grid_sync(no_post);
-          fold_phase(P.part_o, P.so, H, P.ln2[l]);
+        for (int l = 0; l < L; ++l) {
+          const int st = stamp_of(step, l);
+          epi_partials(kPhQ, P.pq2, P.qkv_n, st);
+          attention_phase(l, st);
+          if (plan.n[kPhO] > 0) stage_attn(st);
+          epi_partials(kPhO, P.po2, H, st);
+          fold_phase(P.po2, P.so, st, H, P.ln2[l]);
           grid_sync([&] { load_bop_full(xmap, plan.n[kPhG] > 0); });
-        } else {
-          grid_sync(no_post);
-          if (plan.n[kPhG] > 0) fold_stage(P.part_o, P.so, H, P.ln2[l], -1);
-        }
-        // ---- gate/up + SwiGLU
-        epi_swiglu();
-        grid_sync([&] { load_bop_split(amap, kPhD); });
-        if (fold_cta && plan.fold_g) write_back_h();
-        // ---- down
-        epi_partials(kPhD, P.part_d, H);
-        if (!fold_cta) {
-          grid_sync(no_post);
+          epi_swiglu(st);
+          grid_sync([&] { load_bop_split(amap, kPhD); });
+          epi_partials(kPhD, P.pd2, H, st);
           const bool last = l + 1 == L;
-          fold_phase(P.part_d, P.sd, H, last ? P.final_norm : P.ln1[l + 1]);
+          fold_phase(P.pd2, P.sd, st, H, last ? P.final_norm : P.ln1[l + 1]);
           if (last) grid_sync([&] { load_bop_full(xmap, n_head_tiles > 0); });
           else grid_sync([&] { load_bop_split(xmap, kPhQ); });
-        } else {
-          grid_sync(no_post);
         }
       }
       // ---- lm_head
-      if (fold_cta && n_head_tiles > 0) fold_stage(L > 0 ? P.part_d : nullptr, L > 0 ? P.sd : 0, H, P.final_norm, -1);
       epi_head();
       grid_sync(no_post);
       // ---- sampler (+ tests: keep every step's logits)
@@ -841,11 +1077,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 2 * NT < 32 ? 32 : 2 * NT);
+  if (warp == 9) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static size_t tc_union_bytes(int nt) { return size_t(14) * nt * 128 + (nt == 16 ? 16 * 1024 : 0); }
+static size_t tc_union_bytes(int nt) {
+  size_t u = size_t(14) * nt * 128 + (nt == 16 ? 20 * 1024 : 0);   // B chunks (+ fold_in_cta: fp32 rows and the norm weights)
+  const size_t att = (sizeof(TcAttnSmem) + 1023) & ~size_t(1023);
+  return u > att ? u : att;
+}
 
 size_t tc_smem_bytes(int nt) {
   const size_t budget = 227 * 1024;
@@ -949,7 +1189,7 @@ int launch_decode_tc(TcParams& P, int B, int num_sms, int max_split_chunks, cuda
   // attention items: (sequence, kv head, split) -> one CTA each
   int cap = num_sms / (B * P.n_kv);
   if (cap < 1) return set_error(NT_ERR_INVALID, "decode_tc: %d sequences x %d kv heads exceed %d SMs", B, P.n_kv, num_sms);
-  if (cap > 16) cap = 16;
+  if (cap > 8) cap = 8;   // the merge fetches all (m, l, o) partials of an element in one batch of loads
   if (cap > P.max_splits) cap = P.max_splits;
   P.split_cap = cap;
   const int nt = B <= 16 ? 16 : (B <= 32 ? 32 : 64);
@@ -957,7 +1197,7 @@ int launch_decode_tc(TcParams& P, int B, int num_sms, int max_split_chunks, cuda
   if (sizeof(TcAttnSmem) > tc_union_bytes(nt)) return set_error(NT_ERR_INVALID, "decode_tc: attention staging does not fit");
   const bool hilo = B <= 8;
   const char* fe = getenv("NT_TC_FOLD");   // experiments: "phase" forces the fold phases at small batch
-  P.fold_in_cta = (B <= 4 && size_t(B) * P.hidden * 4 <= 16 * 1024 && !(fe && fe[0] == 'p')) ? 1 : 0;
+  P.fold_in_cta = (B <= 4 && size_t(B) * P.hidden * 4 <= 16 * 1024 && P.hidden <= 1024 && !(fe && fe[0] == 'p')) ? 1 : 0;
   if (hilo) return launch_tc<16, true>(P, num_sms, stream);
   if (nt == 16) return launch_tc<16, false>(P, num_sms, stream);
   if (nt == 32) return launch_tc<32, false>(P, num_sms, stream);

@@ -1,9 +1,9 @@
 // Parameter block + work plan of the persistent tcgen05 decode kernel (lm_decode_tc.cu): ONE cooperative launch
 // runs every layer, the lm_head, the sampler and the whole multi-step decode loop for batch 1..64.
 #pragma once
-#include "lm_kernels.cuh"
+#include <cuda.h>
 
-struct CUtensorMap_st;
+#include "lm_kernels.cuh"
 
 namespace nt {
 
@@ -29,6 +29,7 @@ struct TcPlan {
 };
 
 struct TcParams {
+  alignas(64) CUtensorMap kvmap;  // the paged KV pool as rows of 64 bf16 (box 64 x 64, SWIZZLE_128B); re-encoded when the pool moves
   // model
   int n_layers, total_layers, hidden, inter, n_heads, n_kv, qkv_n, vocab, B;
   float eps, scale_log2;
@@ -42,12 +43,17 @@ struct TcParams {
   const float* final_norm;
   const float* inv_freq;
   // activations
-  float* h;                       // [B][hidden] residual stream (fp32)
+  float* h;                       // [B][hidden] residual stream (fp32): prefill hand-off, sampler output, fold phases
   __nv_bfloat16* xa;              // normalised GEMM input rows: batch <= 8: rows b = hi, 8 + b = lo (bf16 split)
-  __nv_bfloat16* act;             // SwiGLU output rows, same row convention
-  float *part_q, *part_o, *part_d;  // split-K partial sums [slice][B][rows]
+  __nv_bfloat16* act;             // SwiGLU output rows, same row convention (batch > 4)
+  // Hand-off buffers hold (value, stamp) pairs written with one 8-byte store: the consumer polls the data itself
+  // until every pair carries the stamp of the (step, layer) it waits for -- no fence, no flag, no grid barrier.
+  float2 *pq2, *po2, *pd2;        // split-K partial sums [slice][B][rows]
   int sq, so, sd;                 // slices per phase
-  float *att_o, *att_ml;          // split-KV attention partials [B][n_heads][max_splits][64] / [..][2]
+  float2 *ao2, *aml2;             // split-KV attention partials [B][n_heads][max_splits][64] / [..][2] = ((m, .), (l, .))
+  float2* act2;                   // batch <= 4: SwiGLU output [B][inter] (fp32 value, stamp)
+  float2* h2;                     // batch <= 4: residual stream, ping-pong [2][B][hidden]
+  int stamp_base, hstamp_base;    // stamps of this launch lie above these (host counters)
   int max_splits, split_cap;
   KVLayout kv;
   float* logits;                  // [B][vocab]

@@ -263,6 +263,25 @@ NT_DEVINL void gemv_consume_stage(const GemvParams& p, const uint8_t* st, const 
   }
 }
 
+// ---- legacy tensor-core path used by both attention kernels (tcgen05 needs 64+ rows of M; these tiles have 7-16)
+NT_DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+NT_DEVINL void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+NT_DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+
 // =================================================================================== decode attention
 struct AttnSmem {
   __nv_bfloat16 k[64 * 64];
@@ -771,8 +790,8 @@ NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint3
         const int cached = __ldcg(p.seq_lens + b) + p.advance;  // decode: this step's input token is now in the KV cache
         if (p.advance) p.seq_lens[b] = cached;
         const int total = cached + 1;  // tokens in context once `tok` is appended
-        if (tok == p.sp.eos_id || ngen + 1 >= p.sp.max_new_tokens || ngen + 1 >= p.max_new || total >= p.max_ctx)
-          p.done[b] = 1;
+        const int lim = p.sp.limits ? min(p.sp.max_new_tokens, __ldg(p.sp.limits + b)) : p.sp.max_new_tokens;
+        if (tok == p.sp.eos_id || ngen + 1 >= lim || ngen + 1 >= p.max_new || total >= p.max_ctx) p.done[b] = 1;
       }
     }
   }

@@ -163,28 +163,10 @@ int launch_gemv(const GemvParams& p, int nb, int num_sms, cudaStream_t stream) {
   return launch_kernel(kern, dim3(grid), dim3(kGemvThreads), plan.total, stream, true, p, plan);
 }
 
-// ---- legacy tensor-core path used by both attention kernels (tcgen05 needs 64+ rows of M; these tiles have 7-16)
-NT_DEVINL void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-NT_DEVINL void ldmatrix_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-NT_DEVINL void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(addr));
-}
-
 // One TMA descriptor over the whole paged KV pool viewed as rows of 64 bf16 (a K or V page of one head = 64 rows,
 // box = 64 rows x 128 bytes, SWIZZLE_128B).  Row of (layer, k|v, page, head, token):
 //   ((layer * 2 + is_v) * num_pages + page) * n_kv_heads + head) * 64 + token
-static int kv_pool_tmap(const KVLayout& kv, int n_layers, CUtensorMap* out) {
+int kv_pool_tmap(const KVLayout& kv, int n_layers, CUtensorMap* out) {
   static std::mutex mu;
   static CUtensorMap cached;
   static const void* c_base = nullptr;

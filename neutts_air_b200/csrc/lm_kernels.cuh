@@ -115,6 +115,8 @@ struct AttnPrefillParams {
   int max_len;
 };
 int launch_attn_prefill(const AttnPrefillParams& p, int B, int n_layers, cudaStream_t s);
+// one TMA descriptor (box 64 rows x 128 B, SWIZZLE_128B) over the whole paged KV pool viewed as rows of 64 bf16
+int kv_pool_tmap(const KVLayout& kv, int n_layers, ::CUtensorMap_st* out);
 int launch_gather_rows(const float* src, const int32_t* rows, int n, int cols, float* dst, cudaStream_t s);
 
 }  // namespace nt

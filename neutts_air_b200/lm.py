@@ -66,9 +66,13 @@ def pack_weights(shape: LMShape, sd: dict, device) -> dict:
     for i in range(shape.num_layers):
         p = f"model.layers.{i}."
         wq, wk, wv = g(p + "self_attn.q_proj.weight"), g(p + "self_attn.k_proj.weight"), g(p + "self_attn.v_proj.weight")
-        bq, bk, bv = g(p + "self_attn.q_proj.bias"), g(p + "self_attn.k_proj.bias"), g(p + "self_attn.v_proj.bias")
+        zb = lambda w_: torch.zeros(w_.shape[0], dtype=torch.float32)     # Llama-style checkpoints carry no q/k/v bias
+        bq = sd.get(p + "self_attn.q_proj.bias", None)
+        bk = sd.get(p + "self_attn.k_proj.bias", None)
+        bv = sd.get(p + "self_attn.v_proj.bias", None)
+        bq, bk, bv = (bq if bq is not None else zb(wq)), (bk if bk is not None else zb(wk)), (bv if bv is not None else zb(wv))
         out["wqkv"].append(bf(torch.cat((wq[pq], wk[pk], wv), dim=0)))
-        out["bqkv"].append(f32(torch.cat((bq[pq], bk[pk], bv), dim=0)))
+        out["bqkv"].append(f32(torch.cat((bq.float()[pq], bk.float()[pk], bv.float()), dim=0)))
         out["wo"].append(bf(g(p + "self_attn.o_proj.weight")))
         wg, wu = g(p + "mlp.gate_proj.weight"), g(p + "mlp.up_proj.weight")
         out["wgu"].append(bf(torch.stack((wg, wu), dim=1).reshape(2 * wg.shape[0], wg.shape[1])))
@@ -162,8 +166,18 @@ class SpeechLM:
 
     # ------------------------------------------------------------------ low-level steps
     def sampling(self, eos_id: int, min_new_tokens: int = 50, max_new_tokens: int | None = None, top_k: int = 50,
-                 temperature: float = 1.0, seed: int = 0, greedy: bool = False, forced: torch.Tensor | None = None):
+                 temperature: float = 1.0, seed: int = 0, greedy: bool = False, forced: torch.Tensor | None = None,
+                 limits=None, slot_base: int = 0):
+        """``limits``: optional per-sequence caps on generated tokens (list / tensor, one per slot);
+        ``slot_base``: global index of slot 0, so that chunks of a larger batch and ranks of a distributed job
+        draw from independent Philox streams under one seed."""
         mnt = min(max_new_tokens or self.max_new, self.max_new)
+        lptr = None
+        if limits is not None:
+            lt = torch.full((self.max_batch,), mnt, dtype=torch.int32)
+            lt[: len(limits)] = torch.as_tensor(list(limits), dtype=torch.int32)
+            self.limits = lt.to(self.device)
+            lptr = self.limits.data_ptr()
         fptr = None
         if forced is not None:
             f = torch.zeros(self.max_batch, self.max_new, dtype=torch.int32, device=self.device)
@@ -171,7 +185,7 @@ class SpeechLM:
             self.forced = f
             fptr = f.data_ptr()
         return _lib.Sampling(int(eos_id), int(min_new_tokens), int(mnt), int(top_k), float(temperature), int(seed),
-                             int(bool(greedy)), fptr)
+                             int(bool(greedy)), fptr, lptr, int(slot_base))
 
     def prefill(self, prompts, sp, return_logits: bool = False):
         """prompts: list of 1-D int sequences.  Fills the KV cache and samples the first token."""
@@ -251,7 +265,7 @@ class SpeechLM:
     # ------------------------------------------------------------------ generation
     def generate_batch(self, prompts, eos_token_id: int, max_length: int | None = None, min_new_tokens: int = 50,
                        temperature: float = 1.0, top_k: int = 50, max_new_tokens: int | None = None, seed: int = 0,
-                       greedy: bool = False, forced: torch.Tensor | None = None, check_every: int = 32):
+                       greedy: bool = False, forced: torch.Tensor | None = None, check_every: int = 32, slot_base: int = 0):
         """Returns a list of int64 CPU tensors with the generated ids of each prompt (EOS included
         when it was sampled), following transformers' stopping rules (stopping_criteria.py:73-84,
         467-471): stop at EOS or when prompt + generated reaches max_length."""
@@ -259,11 +273,14 @@ class SpeechLM:
         if max_length > self.max_ctx:
             raise ValueError(f"max_length {max_length} exceeds the engine context {self.max_ctx}")
         lens = [len(p) for p in prompts]
-        budget = min(max_length - n for n in lens)
-        if budget < 1:
+        if min(max_length - n for n in lens) < 1:
             raise ValueError("prompt already at max_length")
-        limit = min(budget, max_new_tokens or budget, self.max_new)
-        sp = self.sampling(eos_token_id, min_new_tokens, limit, top_k, temperature, seed, greedy, forced)
+        # max_length counts prompt + generated PER SEQUENCE (stopping_criteria.py:73-84): a long prompt in the batch
+        # must not shorten its neighbours, so every slot gets its own cap and the loop runs to the largest one
+        caps = [min(max_length - n, max_new_tokens or max_length, self.max_new) for n in lens]
+        limit = max(caps)
+        sp = self.sampling(eos_token_id, min_new_tokens, limit, top_k, temperature, seed, greedy, forced,
+                           limits=caps if min(caps) < limit else None, slot_base=slot_base)
         self.prefill(prompts, sp)
         remaining = limit - 1
         B = len(prompts)

@@ -56,10 +56,24 @@ def load_speech_lm(repo: str, device="cuda", **kw) -> SpeechLM:
     root = resolve_repo(repo)
     cfg = json.loads((root / "config.json").read_text())
     arch = (cfg.get("architectures") or ["Qwen2ForCausalLM"])[0]
-    if "Qwen2" not in arch and cfg.get("model_type") not in ("qwen2",):
-        raise ValueError(f"unsupported backbone architecture {arch!r}: the B200 kernels implement the Qwen2 decoder")
+    # the kernels implement the pre-norm RMSNorm / RoPE (half-split) / GQA / SwiGLU decoder that Qwen2, Llama and
+    # Mistral share; q/k/v biases are optional (absent in Llama-style checkpoints -> zeros)
+    family = ("Qwen2", "Llama", "Mistral", "Qwen3")
+    if not any(f in arch for f in family) and cfg.get("model_type") not in ("qwen2", "llama", "mistral"):
+        raise ValueError(f"unsupported backbone architecture {arch!r}: the B200 kernels implement the "
+                         f"Qwen2/Llama-family decoder (RMSNorm, RoPE, GQA, SwiGLU)")
+    if cfg.get("rope_scaling") not in (None, {}) and (cfg["rope_scaling"] or {}).get("rope_type", "default") != "default":
+        raise ValueError("scaled RoPE variants are not implemented")
+    sd = read_state_dict(root)
     shape = LMShape.from_hf_config(cfg)
-    return SpeechLM(shape, read_state_dict(root), device=device, **kw)
+    # tied embeddings: trust the tensors, not a missing config key (a real lm_head must not be dropped silently)
+    if "lm_head.weight" in sd and "model.embed_tokens.weight" in sd:
+        same = sd["lm_head.weight"].shape == sd["model.embed_tokens.weight"].shape and bool(
+            torch.equal(sd["lm_head.weight"], sd["model.embed_tokens.weight"]))
+        shape.tie_embeddings = same
+    elif "lm_head.weight" not in sd:
+        shape.tie_embeddings = True
+    return SpeechLM(shape, sd, device=device, **kw)
 
 
 # ---- NeuCodec decoder: upstream module names (neucodec / XCodec2 lineage) -> oracle-style dict ----
@@ -105,4 +119,6 @@ def codec_weights_from_state_dict(sd: dict) -> tuple:
 def load_codec_decoder(repo: str, device="cuda", **kw) -> CodecDecoder:
     root = resolve_repo(repo)
     shape, w = codec_weights_from_state_dict(read_state_dict(root))
-    return CodecDecoder(shape, w, device=device, **kw)
+    dec = CodecDecoder(shape, w, device=device, **kw)
+    dec.repo = str(repo)     # encode_code() delegates to neucodec.from_pretrained(repo)
+    return dec

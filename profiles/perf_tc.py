@@ -46,24 +46,40 @@ if timeline and impl == "tc":
     lm.prefill(prompts, sp)
     lm.decode(40, sp)
     torch.cuda.synchronize()
-    t = buf[:1024].cpu().tolist()
-    t = [x for x in t if x]
-    d = [(t[i + 1] - t[i]) / 1e3 for i in range(len(t) - 1)]
-    L = shape.num_layers
-    fold_cta = B <= 4 and os.environ.get("NT_TC_FOLD", "")[:1] != "p"
-    if fold_cta:
-        names = ["qkv", "attn", "o", "gu", "down"]
-        per, off = 5, 0
-    else:
-        names = ["qkv", "attn", "o", "fold2", "gu", "down", "fold1"]
-        per, off = 7, 1
-    print(f"TIMELINE marks={len(t)} step total {(t[-1] - t[0]) / 1e3:.1f} us")
-    if off:
-        print(f"  first fold: {d[0]:.2f} us")
-    acc = [0.0] * per
-    for l in range(L):
-        for j in range(per):
-            acc[j] += d[off + l * per + j]
-    print("  per layer (avg us): " + ", ".join(f"{n} {a / L:.2f}" for n, a in zip(names, acc)) + f" | sum {sum(acc) / L:.2f}")
-    rest = d[off + L * per:]
-    print("  tail (lm_head, sampler): " + ", ".join(f"{x:.2f}" for x in rest))
+    names = {0: "step start", 1: "fold: start", 2: "fold: polled", 4: "fold: staged", 5: "fold: bop ready", 10: "epilogue: accumulator ready",
+             21: "attn: page issued", 22: "attn: qkv polled", 23: "attn: page landed", 25: "attn: stored", 31: "merge: polled+staged",
+             32: "merge: bop ready", 41: "act: polled+staged", 42: "act: bop ready", 50: "swiglu: accumulator ready",
+             100: "PHASE qkv done", 101: "PHASE attention done", 102: "PHASE o_proj done", 103: "PHASE gate/up done", 104: "PHASE down done",
+             200: "grid barrier released"}
+    for cta in (0, 1):
+        raw = buf[cta * 1024: cta * 1024 + 1024].cpu().tolist()
+        ts, ids = raw[:512], raw[512:]
+        n = sum(1 for x in ts if x)
+        ts, ids = ts[:n], ids[:n]
+        print(f"TIMELINE cta {cta}: {n} marks, step total {(ts[-1] - ts[0]) / 1e3:.1f} us")
+        L = shape.num_layers
+        # per-phase averages from the phase marks
+        acc, last = {}, ts[0]
+        for tt, i in zip(ts, ids):
+            if i >= 100:
+                acc.setdefault(i, []).append((tt - last) / 1e3)
+                last = tt
+        print("  avg us between phase marks: " + ", ".join(f"{names.get(i, i)} {sum(v) / len(v):.2f} (x{len(v)})" for i, v in sorted(acc.items())))
+        # the fine-grained layer
+        fine = [(tt, i) for tt, i in zip(ts, ids)]
+        start = None
+        for j, (tt, i) in enumerate(fine):
+            if i in (1, 21, 31, 41, 50, 10) and start is None and any(k[1] < 100 for k in fine[j:j + 2]):
+                start = j
+                break
+        if start is not None:
+            j = start
+            t0 = fine[j - 1][0] if j > 0 else fine[j][0]
+            print("  fine-grained layer (us since previous phase mark):")
+            while j < len(fine) and not (fine[j][1] == 104):
+                print(f"    +{(fine[j][0] - t0) / 1e3:7.2f}  {names.get(fine[j][1], fine[j][1])}")
+                j += 1
+                if j - start > 60:
+                    break
+            if j < len(fine):
+                print(f"    +{(fine[j][0] - t0) / 1e3:7.2f}  {names.get(fine[j][1], fine[j][1])}")
