@@ -24,6 +24,17 @@ constexpr int kWarp = 32;
 
 NT_DEVINL uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 NT_DEVINL int lane_id() { return threadIdx.x & 31; }
+// One lane of a fully converged warp (the same lane on every call).  Code issuing uniform-datapath instructions
+// (tcgen05.mma / commit, TMA) must sit under THIS predicate inside warp-uniform control flow: behind a plain
+// `if (lane == 0)` the compiler cannot prove that a single thread is active and wraps every such instruction in an
+// ELECT / BRA.U.ANY loop with R2UR moves -- measured ~160 cycles per tcgen05.mma issue instead of back-to-back issue.
+NT_DEVINL bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// value of lane 0, which the compiler then knows to be warp-uniform
+NT_DEVINL int uniform(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 NT_DEVINL int warp_id() { return threadIdx.x >> 5; }
 
 // ---------------------------------------------------------------- PDL (griddepcontrol)

@@ -63,7 +63,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* acc_bar = bars + 2 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
 
-  const int warp = warp_id();
+  const int warp = uniform(warp_id());   // provably warp-uniform: role branches below stay convergent (elect_one())
   const int lane = lane_id();
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * Cfg::BM;
@@ -94,25 +94,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // kernel ever writes -- while the previous kernel is still finishing.
   pdl_launch_dependents();
   const int early = ep.w_const ? min(STAGES, kb_hi - kb_lo) : 0;
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < early; ++i) {
-      mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
-      tma_load_2d(tiles + i * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, (kb_lo + i) * BK_ELEMS, n0, &full_bar[i]);
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int i = 0; i < early; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
+        tma_load_2d(tiles + i * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, (kb_lo + i) * BK_ELEMS, n0, &full_bar[i]);
+      }
     }
   }
   pdl_wait();  // inputs (A, residual) may come from the previous kernel in the stream
 
+  // Producer and MMA warps: warp-uniform loops, the TMA / tcgen05 instructions under the elect.sync predicate (see
+  // elect_one() in common.cuh: behind `if (lane == 0)` every UTCHMMA costs ~160 cycles of issue overhead).
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      for (int kb = kb_lo; kb < kb_hi; ++kb) {
-        const int s = (kb - kb_lo) % STAGES;
-        const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
-        const bool b_in_flight = (kb - kb_lo) < early;
-        if (!b_in_flight) {
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        }
+    const bool leader = elect_one();
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+      const int s = (kb - kb_lo) % STAGES;
+      const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
+      const bool b_in_flight = (kb - kb_lo) < early;
+      if (!b_in_flight) mbar_wait(&empty_bar[s], ph ^ 1);
+      if (leader) {
+        if (!b_in_flight) mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         uint8_t* sa = tiles + s * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
         const int tap = kb / kb_per_tap;
@@ -123,14 +126,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(kFmt, 128, BN);
-      for (int kb = kb_lo; kb < kb_hi; ++kb) {
-        const int s = (kb - kb_lo) % STAGES;
-        const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(tiles + s * Cfg::STAGE_BYTES);
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc(kFmt, 128, BN);
+    const uint32_t tiles_addr = smem_u32(tiles);
+    for (int kb = kb_lo; kb < kb_hi; ++kb) {
+      const int s = (kb - kb_lo) % STAGES;
+      const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (leader) {
+        const uint32_t sa = tiles_addr + static_cast<uint32_t>(s) * Cfg::STAGE_BYTES;
         const uint32_t sb = sa + Cfg::A_BYTES;
         const uint64_t adesc = umma_desc_sw128(sa);
         const uint64_t bdesc = umma_desc_sw128(sb);
@@ -144,8 +149,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
       }
-      umma_commit(acc_bar);  // accumulator complete
     }
+    if (leader) umma_commit(acc_bar);  // accumulator complete
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int q = warp - 4;  // TMEM lane quarter (== warp % 4)

@@ -101,13 +101,16 @@ struct nt_lm {
   long long* prof = nullptr;          // megakernel timeline buffer (profiles/probe_mega.py)
   int prof_step = 0;
   // persistent tcgen05 decode kernel (lm_decode_tc.cu): plan, tensor maps and buffers live in the workspace
-  bool tc_ok = false;
-  int tc_sq = 0, tc_so = 0, tc_sd = 0, tc_ntiles = 0, tc_chunks = 0, tc_rows = 0;
+  bool tc_ok = false, tc_flat_ok = false;
+  TcPlanInfo tc_info[2] = {};         // [0]: whole-K gate/up plan (any batch), [1]: flat plan (batch <= 4)
+  int tc_rows = 0;
+  unsigned char* tc_gu_nsl = nullptr; // flat plan: K slices per gate/up tile
   uint8_t* tc_maps = nullptr;         // CUtensorMap[4 * n_layers + 1] weights, then xa x {16,32,64}, act x {16,32,64}
   TcPlan* tc_plan = nullptr;
   __nv_bfloat16 *tc_xa = nullptr, *tc_act = nullptr;
   float *tc_tmax = nullptr;
-  float2 *tc_pq2 = nullptr, *tc_po2 = nullptr, *tc_pd2 = nullptr, *tc_ao2 = nullptr, *tc_aml2 = nullptr, *tc_act2 = nullptr, *tc_h2 = nullptr;
+  float2 *tc_pq2 = nullptr, *tc_po2 = nullptr, *tc_pd2 = nullptr, *tc_ao2 = nullptr, *tc_aml2 = nullptr, *tc_act2 = nullptr, *tc_pg2 = nullptr,
+         *tc_h2 = nullptr;
   size_t tc_pair_bytes = 0;           // extent of the stamped buffers (contiguous, starting at tc_pq2)
   int tc_stamp = 0, tc_hstamp = 0;    // stamps handed out so far (see TcParams::stamp_base)
 };
@@ -153,7 +156,8 @@ static size_t lm_carve(const nt_lm_config& c, void* ws, size_t bytes, F&& assign
     (L)->splitk_ws = a.take<float>(size_t(8) * 128 * (qkv_n > H ? qkv_n : H));                 \
     (L)->tc_rows = c.max_batch < kTcMaxBatch ? c.max_batch : kTcMaxBatch;                      \
     (L)->tc_maps = a.take<uint8_t>(size_t(128) * (size_t(4) * c.n_layers + 1 + 6));            \
-    (L)->tc_plan = a.take<TcPlan>(256);                                                        \
+    (L)->tc_plan = a.take<TcPlan>(512);                                                        \
+    (L)->tc_gu_nsl = a.take<unsigned char>(4096);                                              \
     (L)->tc_xa = a.take<__nv_bfloat16>(size_t(kTcMaxBatch) * H);                               \
     (L)->tc_act = a.take<__nv_bfloat16>(size_t(kTcMaxBatch) * I);                              \
     (L)->tc_tmax = a.take<float>(size_t((L)->tc_rows) * ((V + 127) / 128));                    \
@@ -163,6 +167,7 @@ static size_t lm_carve(const nt_lm_config& c, void* ws, size_t bytes, F&& assign
     (L)->tc_ao2 = a.take<float2>(size_t((L)->tc_rows) * c.n_heads * max_splits * 64);          \
     (L)->tc_aml2 = a.take<float2>(size_t((L)->tc_rows) * c.n_heads * max_splits * 2);          \
     (L)->tc_act2 = a.take<float2>(size_t(4) * I);                                              \
+    (L)->tc_pg2 = a.take<float2>(size_t(kTcMaxGuSlices) * 4 * 2 * I);                          \
     (L)->tc_h2 = a.take<float2>(size_t(2) * 4 * H);                                            \
     (L)->tc_pair_bytes = size_t(reinterpret_cast<uint8_t*>((L)->tc_h2 + size_t(2) * 4 * H) - reinterpret_cast<uint8_t*>((L)->tc_pq2)); \
   }
@@ -266,10 +271,13 @@ extern "C" int nt_lm_create(const nt_lm_config* cfg, const nt_lm_weights* w, voi
   {
     // persistent tcgen05 decode kernel: work plan + every tensor map, built once (maps were
     // re-encoded on every GEMM call).  A shape the plan cannot take leaves tc_ok false -> older decode paths.
-    std::vector<TcPlan> plan(256);
+    std::vector<TcPlan> plan(512);
+    std::vector<unsigned char> nsl(4096, 0);
     TcShape ts{c.hidden, c.inter, c.n_heads, c.n_kv_heads, lm->qkv_n, c.vocab_size};
     const int G = lm->num_sms > 256 ? 256 : lm->num_sms;
-    if (tc_build_plan(ts, G, plan.data(), &lm->tc_sq, &lm->tc_so, &lm->tc_sd, &lm->tc_ntiles, &lm->tc_chunks) == NT_OK) {
+    lm->tc_flat_ok = (2 * c.inter + 127) / 128 <= 4096 && !env_flag("NT_TC_NO_FLAT") &&
+                     tc_build_plan(ts, G, true, plan.data() + 256, nsl.data(), &lm->tc_info[1]) == NT_OK;
+    if (tc_build_plan(ts, G, false, plan.data(), nullptr, &lm->tc_info[0]) == NT_OK) {
       const size_t nmaps = size_t(4) * c.n_layers + 1 + 6;
       std::vector<CUtensorMap> maps(nmaps);
       const int HD = c.n_heads * 64;
@@ -288,7 +296,8 @@ extern "C" int nt_lm_create(const nt_lm_config* cfg, const nt_lm_weights* w, voi
       }
       static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
       if (!mrc && cudaMemcpy(lm->tc_maps, maps.data(), nmaps * sizeof(CUtensorMap), cudaMemcpyHostToDevice) == cudaSuccess &&
-          cudaMemcpy(lm->tc_plan, plan.data(), 256 * sizeof(TcPlan), cudaMemcpyHostToDevice) == cudaSuccess &&
+          cudaMemcpy(lm->tc_plan, plan.data(), 512 * sizeof(TcPlan), cudaMemcpyHostToDevice) == cudaSuccess &&
+          cudaMemcpy(lm->tc_gu_nsl, nsl.data(), nsl.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
           cudaMemset(lm->tc_xa, 0, size_t(kTcMaxBatch) * c.hidden * 2) == cudaSuccess &&
           cudaMemset(lm->tc_act, 0, size_t(kTcMaxBatch) * c.inter * 2) == cudaSuccess &&
           cudaMemset(lm->tc_pq2, 0, lm->tc_pair_bytes) == cudaSuccess)   // stamp 0 = "never written"
@@ -565,7 +574,11 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
   // NT_DECODE_IMPL = tc (default: persistent tcgen05 kernel, every batch size) | mega | perop (round-1 paths, kept
   // for A/B measurements and as the fallback for shapes the tcgen05 plan does not take)
   const char* impl = getenv("NT_DECODE_IMPL");
-  const bool want_tc = !impl || !impl[0] || impl[0] == 't';
+  // default: the tcgen05 kernel up to NT_TC_MAX_BATCH sequences (measured on B200: 1.03 ms / step at batch 8 against
+  // 1.23 ms for the per-op chain; from batch 16 the chain's step time (1.25 - 1.31 ms, flat in the batch) wins)
+  int tc_cap = 8;
+  if (const char* e = getenv("NT_TC_MAX_BATCH")) tc_cap = atoi(e);
+  const bool want_tc = (impl && impl[0] == 't') || ((!impl || !impl[0]) && B <= tc_cap);
   const int tc_layers = lm->debug_layers >= 0 ? lm->debug_layers : c.n_layers;
   if (want_tc && lm->tc_ok && B <= lm->tc_rows && B * c.n_kv_heads <= lm->num_sms && !env_flag("NT_NO_MEGA")) {
     TcParams P;
@@ -576,12 +589,15 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(lm->tc_maps);
     const int nti = B <= 16 ? 0 : (B <= 32 ? 1 : 2);
     P.wmaps = maps, P.xmap = maps + 4 * c.n_layers + 1 + nti, P.amap = maps + 4 * c.n_layers + 4 + nti;
-    P.plan = lm->tc_plan;
+    const int pi = (lm->tc_flat_ok && tc_fold_in_cta(B, c.hidden)) ? 1 : 0;
+    const TcPlanInfo& info = lm->tc_info[pi];
+    P.plan = lm->tc_plan + 256 * pi;
+    P.pg2 = lm->tc_pg2, P.gu_nsl = lm->tc_gu_nsl;
     P.ln1 = lm->ptr_tab, P.bqkv = lm->ptr_tab + c.n_layers, P.ln2 = lm->ptr_tab + 2 * c.n_layers;
     P.final_norm = lm->final_norm, P.inv_freq = lm->inv_freq;
     P.h = lm->h, P.xa = lm->tc_xa, P.act = lm->tc_act;
     P.pq2 = lm->tc_pq2, P.po2 = lm->tc_po2, P.pd2 = lm->tc_pd2;
-    P.sq = lm->tc_sq, P.so = lm->tc_so, P.sd = lm->tc_sd;
+    P.sq = info.sq, P.so = info.so, P.sd = info.sd;
     P.ao2 = lm->tc_ao2, P.aml2 = lm->tc_aml2, P.act2 = lm->tc_act2, P.h2 = lm->tc_h2, P.max_splits = lm->max_splits;
     // (value, stamp) hand-offs: every launch takes a fresh range of stamps, so nothing left in the buffers by an
     // earlier launch (or by another batch size) can ever match
@@ -594,7 +610,7 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
     lm->tc_stamp += need_s, lm->tc_hstamp += need_h;
     P.kv = make_kv(lm, st);
     if ((rc = kv_pool_tmap(P.kv, c.n_layers, &P.kvmap))) return rc;
-    P.logits = lm->logits, P.tmax = lm->tc_tmax, P.ntiles = lm->tc_ntiles;
+    P.logits = lm->logits, P.tmax = lm->tc_tmax, P.ntiles = info.ntiles;
     P.samp = make_sampler(lm, st, sp);
     P.samp.advance = 1;
     P.gbar = lm->gbar;
@@ -603,7 +619,7 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
     P.logits_step_stride = static_cast<long long>(B) * c.vocab_size;
     P.prof = lm->prof, P.prof_step = lm->prof_step;
     if ((rc = launch_sampler_check(P.samp))) return rc;
-    return launch_decode_tc(P, B, lm->num_sms > 256 ? 256 : lm->num_sms, lm->tc_chunks, stream);
+    return launch_decode_tc(P, B, lm->num_sms > 256 ? 256 : lm->num_sms, info, stream);
   }
   if (B <= mega_max_batch() && !env_flag("NT_NO_MEGA") && !(impl && impl[0] == 'p') && c.hidden % 64 == 0) {
     // Persistent megakernel: every layer, the lm_head, the sampler and all n_steps in one launch.

@@ -31,6 +31,7 @@
 
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <vector>
 
@@ -143,8 +144,8 @@ NT_DEVINL void tc_fold4(const float2* hsrc, int hstamp, const float2* parts, int
 }
 
 constexpr int kPhQ = 0, kPhO = 1, kPhG = 2, kPhD = 3;
+constexpr int kAttWarpsMax = 4;   // most warps that walk KV pages in the attention phase
 
-constexpr int kAttWarps = 4;   // warps that walk KV pages in the attention phase
 
 // shared-memory misc block (after the ring and the union region)
 struct TcMisc {
@@ -153,10 +154,11 @@ struct TcMisc {
   uint64_t bop_bar;
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
-  uint64_t att_bar[kAttWarps];
+  uint64_t att_bar[kAttWarpsMax];
   uint32_t tmem_slot;
   int go;                 // steps released to the stream / MMA warps so far, -1 = stop
   int pos[kTcMaxBatch];   // this step's seq_lens snapshot
+  int apage[32];          // physical pages of this CTA's attention split (this step)
   int mask_eos[kTcMaxBatch];
   float red[64];
   float tile_max[2][4][kTcMaxBatch];
@@ -167,16 +169,13 @@ struct TcMisc {
   TcPlan plan;
 };
 
-// Attention staging: four warps each own a K page + V page buffer (SWIZZLE_128B, filled by TMA) and walk the pages
-// of this CTA's split independently; per-warp partial outputs merge through shared memory.
-struct TcAttnSmem {
-  __nv_bfloat16 k[kAttWarps][64 * 64];   // 8 KB each => 1024-byte aligned inside the 1024-aligned union region
-  __nv_bfloat16 v[kAttWarps][64 * 64];
-  float o[kAttWarps][8][64];             // per-warp unnormalised outputs [head][dim]
-  float ml[kAttWarps][8][2];
-  float q[8][64];                        // this group's queries after bias + RoPE (fp32)
-  float knew[64], vnew[64];              // the new token's K / V row
-};
+// Attention staging (AW = 2 or 4 page-walking warps, TcParams::att_warps): every warp owns a K page + V page buffer
+// (SWIZZLE_128B, filled by TMA; 8 KB each => 1024-byte aligned) and walks the pages of this CTA's split independently;
+// per-warp partial outputs merge through shared memory.  Layout behind att_off:
+//   K[AW][8 KB] | V[AW][8 KB] | o[AW][8][64] f32 | ml[AW][8][2] f32 | q[8][64] f32 | knew[64] | vnew[64]
+__host__ __device__ constexpr size_t tc_attn_layout_bytes(int aw) {
+  return size_t(2) * aw * 8192 + (size_t(aw) * 8 * 64 + size_t(aw) * 8 * 2 + 8 * 64 + 128) * 4;
+}
 
 // ------------------------------------------------------------------------------------------ the kernel
 template <int NT, bool HILO>
@@ -193,7 +192,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
   uint8_t* ring = smem;
   uint8_t* uni = smem + P.uni_off;
   TcMisc* ms = reinterpret_cast<TcMisc*>(smem + P.misc_off);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform(tid >> 5), lane = tid & 31;
   const int NS = P.nstages;
   const int L = P.n_layers;
   const int B = P.B;
@@ -213,7 +212,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       mbar_init(&ms->acc_full[i], 1);
       mbar_init(&ms->acc_empty[i], 4);
     }
-    for (int i = 0; i < kAttWarps; ++i) mbar_init(&ms->att_bar[i], 1);
+    for (int i = 0; i < kAttWarpsMax; ++i) mbar_init(&ms->att_bar[i], 1);
     fence_barrier_init();
     ms->go = 1;
   }
@@ -248,85 +247,96 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
   };
 
   if (warp == 8) {
-    // ================================================================== weight stream (one thread)
-    if (lane == 0) {
-      int slot = 0;
-      uint32_t par = 0;       // parity of the slot's NEXT completion of empty_bar that we must have seen
-      bool wrapped = false;   // ring used at least once
-      auto push = [&](const CUtensorMap* m, int kcol, int row) {
-        if (wrapped) mbar_wait(&ms->empty_bar[slot], par ^ 1);
+    // ================================================================== weight stream
+    // The whole warp walks the plan (warp-uniform control flow); one elected lane issues the copies.
+    const bool leader = elect_one();
+    int slot = 0;
+    uint32_t par = 0;       // parity of the slot's NEXT completion of empty_bar that we must have seen
+    bool wrapped = false;   // ring used at least once
+    auto push = [&](const CUtensorMap* m, int kcol, int row) {
+      if (wrapped) mbar_wait(&ms->empty_bar[slot], par ^ 1);
+      if (leader) {
         mbar_arrive_expect_tx(&ms->full_bar[slot], 16384);
         tma_load_2d(ring + static_cast<size_t>(slot) * 16384, m, kcol, row, &ms->full_bar[slot]);
-        if (++slot == NS) slot = 0, par ^= 1, wrapped = true;
-      };
-      for (int step = 0; step < P.n_steps; ++step) {
-        if (!wait_go(step)) break;
-        for (int l = 0; l < L; ++l)
-          for (int ph = 0; ph < 4; ++ph) {
-            const CUtensorMap* m = wmaps + 4 * l + ph;
-            for (int i = 0; i < plan.n[ph]; ++i) {
-              const TcItem it = plan.it[ph][i];
-              for (int kb = 0; kb < it.nkb; ++kb) push(m, (it.kb0 + kb) * 64, it.tile * 128);
-            }
-          }
-        const CUtensorMap* hm = wmaps + 4 * P.total_layers;
-        for (int t = plan.head_t0; t < plan.head_t1; ++t)
-          for (int kb = 0; kb < KBH; ++kb) push(hm, kb * 64, t * 128);
       }
+      if (++slot == NS) slot = 0, par ^= 1, wrapped = true;
+    };
+    for (int step = 0; step < P.n_steps; ++step) {
+      if (!wait_go(step)) break;
+      for (int l = 0; l < L; ++l)
+        for (int ph = 0; ph < 4; ++ph) {
+          const CUtensorMap* m = wmaps + 4 * l + ph;
+          const int n_it = uniform(plan.n[ph]);
+          for (int i = 0; i < n_it; ++i) {
+            const int tile = uniform(plan.it[ph][i].tile), kb0 = uniform(plan.it[ph][i].kb0), nkb = uniform(plan.it[ph][i].nkb);
+            for (int kb = 0; kb < nkb; ++kb) push(m, (kb0 + kb) * 64, tile * 128);
+          }
+        }
+      const CUtensorMap* hm = wmaps + 4 * P.total_layers;
+      const int t0 = uniform(plan.head_t0), t1 = uniform(plan.head_t1);
+      for (int t = t0; t < t1; ++t)
+        for (int kb = 0; kb < KBH; ++kb) push(hm, kb * 64, t * 128);
     }
   } else if (warp == 9) {
-    // ================================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(1, 128, NT);
-      int slot = 0;
-      uint32_t par = 0;
-      uint32_t bop_n = 0, acc_n = 0;
-      const uint32_t bop_addr = smem_u32(uni);
-      // one item: nkb ring tiles against B chunks chunk0, chunk0 + 1, ...
-      auto run_item = [&](int nkb, int chunk0) {
-        const uint32_t buf = acc_n & 1;
-        mbar_wait(&ms->acc_empty[buf], ((acc_n >> 1) & 1) ^ 1);
+    // ================================================================== MMA issuer
+    // Warp-uniform control flow, tcgen05.mma / commit under the elect.sync predicate: this is what lets the compiler
+    // keep descriptors in uniform registers and issue the MMAs back to back (see elect_one() in common.cuh).
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = umma_idesc(1, 128, NT);
+    int slot = 0;
+    uint32_t par = 0;
+    uint32_t bop_n = 0, acc_n = 0;
+    const uint32_t bop_addr = smem_u32(uni);
+    const uint32_t ring_addr = smem_u32(ring);
+    // one item: nkb ring tiles against B chunks chunk0, chunk0 + 1, ...
+    auto run_item = [&](int nkb, int chunk0) {
+      const uint32_t buf = acc_n & 1;
+      mbar_wait(&ms->acc_empty[buf], ((acc_n >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t dst = tmem_base + buf * ACOLS;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&ms->full_bar[slot], par);
         tc_fence_after();
-        const uint32_t dst = tmem_base + buf * ACOLS;
-        for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&ms->full_bar[slot], par);
-          tc_fence_after();
-          const uint64_t adesc = umma_desc_sw128(smem_u32(ring + static_cast<size_t>(slot) * 16384));
+        if (leader) {
+          const uint64_t adesc = umma_desc_sw128(ring_addr + static_cast<uint32_t>(slot) * 16384u);
           const uint64_t bdesc = umma_desc_sw128(bop_addr + static_cast<uint32_t>(chunk0 + kb) * CHUNK);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(dst + (k % NACC) * NT, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > 0 || k >= NACC) ? 1u : 0u);
           umma_commit(&ms->empty_bar[slot]);
-          if (++slot == NS) slot = 0, par ^= 1;
         }
-        umma_commit(&ms->acc_full[buf]);
-        ++acc_n;
-      };
-      for (int step = 0; step < P.n_steps; ++step) {
-        if (!wait_go(step)) break;
-        for (int l = 0; l < L; ++l)
-          for (int ph = 0; ph < 4; ++ph) {
-            if (plan.n[ph] == 0) continue;
-            mbar_wait(&ms->bop_bar, bop_n & 1);
-            ++bop_n;
-            tc_fence_after();
-            int chunk = 0;
-            for (int i = 0; i < plan.n[ph]; ++i) {
-              const TcItem it = plan.it[ph][i];
-              if (ph == kPhG) {
-                run_item(it.nkb, 0);   // whole K, all items share the staged input
-              } else {
-                run_item(it.nkb, chunk);
-                chunk += it.nkb;
-              }
-            }
-          }
-        if (n_head_tiles > 0) {
+        if (++slot == NS) slot = 0, par ^= 1;
+      }
+      if (leader) umma_commit(&ms->acc_full[buf]);
+      ++acc_n;
+    };
+    const int gu_split = uniform(plan.gu_split);
+    const int n_head = uniform(n_head_tiles);
+    for (int step = 0; step < P.n_steps; ++step) {
+      if (!wait_go(step)) break;
+      for (int l = 0; l < L; ++l)
+        for (int ph = 0; ph < 4; ++ph) {
+          const int n_it = uniform(plan.n[ph]);
+          if (n_it == 0) continue;
           mbar_wait(&ms->bop_bar, bop_n & 1);
           ++bop_n;
           tc_fence_after();
-          for (int t = 0; t < n_head_tiles; ++t) run_item(KBH, 0);
+          int chunk = 0;
+          for (int i = 0; i < n_it; ++i) {
+            const int nkb = uniform(plan.it[ph][i].nkb);
+            if (ph == kPhG && !gu_split) {
+              run_item(nkb, 0);   // whole K, all items share the staged input
+            } else {
+              run_item(nkb, chunk);
+              chunk += nkb;
+            }
+          }
         }
+      if (n_head > 0) {
+        mbar_wait(&ms->bop_bar, bop_n & 1);
+        ++bop_n;
+        tc_fence_after();
+        for (int t = 0; t < n_head; ++t) run_item(KBH, 0);
       }
     }
   } else {
@@ -343,24 +353,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
     const int I = P.inter;
     float* xf = reinterpret_cast<float*>(uni + 14 * CHUNK);   // fold_in_cta: fp32 folded rows [B][H] behind the B chunks
     float* xw = xf + 4096;                                      // ... and the RMSNorm weight row [H] (H <= 1024)
-    TcAttnSmem* asmem = reinterpret_cast<TcAttnSmem*>(uni);
+    const int AW = P.att_warps;
+    uint8_t* att = smem + P.att_off;
+    auto att_k = [&](int w) { return reinterpret_cast<__nv_bfloat16*>(att + static_cast<size_t>(w) * 8192); };
+    auto att_v = [&](int w) { return reinterpret_cast<__nv_bfloat16*>(att + static_cast<size_t>(AW + w) * 8192); };
+    float* att_o = reinterpret_cast<float*>(att + static_cast<size_t>(2 * AW) * 8192);   // [AW][8][64]
+    float* att_ml = att_o + AW * 8 * 64;                                                  // [AW][8][2]
+    float* att_q = att_ml + AW * 8 * 2;                                                   // [8][64]
+    float* att_knew = att_q + 8 * 64;
+    float* att_vnew = att_knew + 64;
+    const bool att_separate = P.att_off != P.uni_off;   // dedicated staging: KV pages are fetched ahead of the phase
     int fold_no = 0;   // fold_in_cta: folds done in this launch (ping-pong parity + stamp of the residual stream)
 
     // ---- grid barrier; `post` runs on thread 0 between the release and the trailing CTA barrier
-    auto grid_sync = [&](auto post) {
+    auto grid_sync = [&](auto post) {   // post runs on the whole of warp 0 (it issues TMA under elect_one())
       csync();
-      if (tid == 0) {
+      if (warp == 0) {
         target += G;
-        __threadfence();
-        atomicAdd(P.gbar, 1u);
-        uint32_t spins = 0;
-        while (tc_ld_acquire(P.gbar) < target) {
-          if (++spins > (1u << 24)) {
-            printf("neutts_b200: decode_tc grid barrier timed out (block %d, target %u, seen %u)\n", blockIdx.x, target, *P.gbar);
-            __trap();
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(P.gbar, 1u);
+          uint32_t spins = 0;
+          while (tc_ld_acquire(P.gbar) < target) {
+            if (++spins > (1u << 24)) {
+              printf("neutts_b200: decode_tc grid barrier timed out (block %d, target %u, seen %u)\n", blockIdx.x, target, *P.gbar);
+              __trap();
+            }
           }
+          prof.mark(200);
         }
-        prof.mark(200);
+        __syncwarp();
         post();
       }
       csync();
@@ -369,18 +391,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
     auto stamp_of = [&](int step, int l) { return P.stamp_base + step * (L + 1) + l + 1; };
 
     // ---- B operand by TMA from global bf16 rows (thread 0, after the barrier that published them)
+    //      (whole warp 0, converged: one elected lane issues)
     auto load_bop_split = [&](const CUtensorMap* m, int ph) {   // chunks of the items' own k ranges, item after item
-      const int n = plan.n[ph];
+      const int n = uniform(plan.n[ph]);
       if (n == 0) return;
-      fence_proxy_async_all();
-      mbar_arrive_expect_tx(&ms->bop_bar, static_cast<uint32_t>(ms->nchunks[ph]) * CHUNK);
-      for (int c = 0; c < ms->nchunks[ph]; ++c) tma_load_2d(uni + c * CHUNK, m, ms->ckb[ph][c] * 64, 0, &ms->bop_bar);
+      const int nch = uniform(ms->nchunks[ph]);
+      const bool leader = elect_one();
+      if (leader) {
+        fence_proxy_async_all();
+        mbar_arrive_expect_tx(&ms->bop_bar, static_cast<uint32_t>(nch) * CHUNK);
+      }
+      for (int c = 0; c < nch; ++c) {
+        const int kb = uniform(ms->ckb[ph][c]);
+        if (leader) tma_load_2d(uni + c * CHUNK, m, kb * 64, 0, &ms->bop_bar);
+      }
     };
     auto load_bop_full = [&](const CUtensorMap* m, bool need) {  // all KBH chunks of the hidden-sized K
-      if (!need) return;
-      fence_proxy_async_all();
-      mbar_arrive_expect_tx(&ms->bop_bar, static_cast<uint32_t>(KBH) * CHUNK);
-      for (int kb = 0; kb < KBH; ++kb) tma_load_2d(uni + kb * CHUNK, m, kb * 64, 0, &ms->bop_bar);
+      if (!uniform(need ? 1 : 0)) return;
+      if (elect_one()) {
+        fence_proxy_async_all();
+        mbar_arrive_expect_tx(&ms->bop_bar, static_cast<uint32_t>(KBH) * CHUNK);
+        for (int kb = 0; kb < KBH; ++kb) tma_load_2d(uni + kb * CHUNK, m, kb * 64, 0, &ms->bop_bar);
+      }
     };
     // thread-staged B operand is complete: every writer fenced its writes towards the async proxy
     auto bop_ready = [&] {
@@ -496,29 +528,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       const int hstamp = P.hstamp_base + fold_no;
       const int nq = H >> 2;
       pm(1);
-      for (int q = tid; q < B * nq; q += kConsumerThreads) {
-        const int b = q / nq, i4 = (q - b * nq) * 4;
-        float acc[4];
-        const float4 nw = __ldg(reinterpret_cast<const float4*>(norm_w + i4));   // in flight together with the slices
-        tc_fold4(hsrc, hstamp, parts, nparts, pstamp, rows, B, H, b, i4, acc);
-        *reinterpret_cast<float4*>(xf + b * H + i4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        if (b == 0) *reinterpret_cast<float4*>(xw + i4) = nw;
+      float ssb[4] = {0.f, 0.f, 0.f, 0.f};   // this thread's share of every row's sum of squares
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (b < B) {
+          for (int q = tid; q < nq; q += kConsumerThreads) {
+            const int i4 = q * 4;
+            float acc[4];
+            const float4 nw = __ldg(reinterpret_cast<const float4*>(norm_w + i4));   // in flight together with the slices
+            tc_fold4(hsrc, hstamp, parts, nparts, pstamp, rows, B, H, b, i4, acc);
+            *reinterpret_cast<float4*>(xf + b * H + i4) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            if (b == 0) *reinterpret_cast<float4*>(xw + i4) = nw;
+            ssb[b] += (acc[0] * acc[0] + acc[1] * acc[1]) + (acc[2] * acc[2] + acc[3] * acc[3]);
+          }
+        }
       }
       pm(2);
-      csync();
-      if (warp < B) {  // warp b: sum of squares of row b
-        float ss = 0.f;
-        for (int i = lane; i < H; i += 32) ss += xf[warp * H + i] * xf[warp * H + i];
-        ss = warp_sum(ss);
-        if (lane == 0) ms->rstd[warp] = rsqrtf(ss / static_cast<float>(H) + P.eps);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (b < B) {
+          const float t = warp_sum(ssb[b]);
+          if (lane == 0) ms->red[b * kConsumerWarps + warp] = t;
+        }
       }
       csync();
+      float rs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        if (b < B) {
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < kConsumerWarps; ++w) t += ms->red[b * kConsumerWarps + w];   // fixed order: every CTA gets the same bits
+          rs[b] = rsqrtf(t / static_cast<float>(H) + P.eps);
+        }
+      }
       const int nch = ph < 0 ? KBH : ms->nchunks[ph];
       const int per = B * 64;
       for (int e = tid; e < nch * per; e += kConsumerThreads) {
         const int c = e / per, r = e - c * per, b = r >> 6, k = r & 63;
         const int i = (ph < 0 ? c : ms->ckb[ph][c]) * 64 + k;
-        const float xn = xw[i] * (xf[b * H + i] * ms->rstd[b]);
+        const float rstd = b == 0 ? rs[0] : (b == 1 ? rs[1] : (b == 2 ? rs[2] : rs[3]));
+        const float xn = xw[i] * (xf[b * H + i] * rstd);
         __nv_bfloat16 hi, lo;
         split_hilo(xn, hi, lo);
         uint8_t* cb = uni + c * CHUNK;
@@ -547,26 +597,54 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
 
     uint32_t att_par = 0;   // parity of this warp's page barrier (warps 0..3)
     const CUtensorMap* kvmap = &P.kvmap;
+    // physical page of logical page pg of this CTA's split (cached at step start)
+    auto page_of = [&](int pg, int p0) -> int {
+      return (pg - p0 < 32) ? ms->apage[pg - p0] : __ldcg(P.kv.page_table + my_b * P.kv.max_pages_per_seq + pg);
+    };
+    auto cache_pages = [&] {   // after ms->pos is set (and a barrier); followed by a barrier
+      if (my_b >= B || tid >= 32) return;
+      const SplitGeom geo = split_geom(ms->pos[my_b], P.kv.max_ctx, split_cap);
+      if (my_split >= geo.nsplit) return;
+      const int p0 = my_split * geo.pps, p1 = min(p0 + geo.pps, geo.npages);
+      if (p0 + tid < p1) ms->apage[tid] = __ldcg(P.kv.page_table + my_b * P.kv.max_pages_per_seq + p0 + tid);
+    };
+    // lane 0 of an attention warp: K and V page of (sequence, kv head) -> this warp's buffers
+    //   (whole attention warp, converged; fence: see the proxy fence after the sampler's grid barrier)
+    auto issue_page = [&](int l, int pg, int p0, bool fence) {
+      const int krow0 = l * 2 * P.kv.num_pages * P.kv.n_kv_heads * 64;
+      const int vrow0 = krow0 + P.kv.num_pages * P.kv.n_kv_heads * 64;
+      const int page = uniform(page_of(pg, p0));
+      if (elect_one()) {
+        if (fence) fence_proxy_async_all();
+        mbar_arrive_expect_tx(&ms->att_bar[warp], 2 * 8192);
+        tma_load_2d(att_k(warp), kvmap, 0, krow0 + (page * P.kv.n_kv_heads + my_kvh) * 64, &ms->att_bar[warp]);
+        tma_load_2d(att_v(warp), kvmap, 0, vrow0 + (page * P.kv.n_kv_heads + my_kvh) * 64, &ms->att_bar[warp]);
+      }
+    };
+    // dedicated staging: the first round of pages of layer l is fetched before the layer's projections run (they do
+    // not depend on them: the new token's row is patched into the staged page)
+    auto attn_prefetch = [&](int l) {
+      if (!att_separate || my_b >= B || warp >= AW) return;
+      const SplitGeom geo = split_geom(uniform(ms->pos[my_b]), P.kv.max_ctx, split_cap);
+      if (my_split >= geo.nsplit) return;
+      const int p0 = my_split * geo.pps, p1 = min(p0 + geo.pps, geo.npages);
+      // no proxy fence here: the rows these pages hold were written in EARLIER steps (this step's row is patched in
+      // shared memory) and every step starts behind a grid barrier + proxy fence
+      if (p0 + warp < p1) issue_page(l, p0 + warp, p0, false);
+    };
     auto attention_phase = [&](int l, int stamp) {
       if (my_b >= B) return;
-      const int pos = ms->pos[my_b];
+      const int pos = uniform(ms->pos[my_b]);
       const SplitGeom geo = split_geom(pos, P.kv.max_ctx, split_cap);
       if (my_split >= geo.nsplit) return;
       const int b = my_b, kvh = my_kvh;
       const int p0 = my_split * geo.pps, p1 = min(p0 + geo.pps, geo.npages);
       const bool appends = pos < P.kv.max_ctx && (pos >> 6) >= p0 && (pos >> 6) < p1;
-      const int krow0 = l * 2 * P.kv.num_pages * P.kv.n_kv_heads * 64;
-      const int vrow0 = krow0 + P.kv.num_pages * P.kv.n_kv_heads * 64;
-      auto issue_page = [&](int pg) {   // lane 0 of an attention warp: K and V page of (sequence, kv head) -> this warp's buffers
-        const int page = __ldcg(P.kv.page_table + b * P.kv.max_pages_per_seq + pg);
-        fence_proxy_async_all();
-        mbar_arrive_expect_tx(&ms->att_bar[warp], 2 * 8192);
-        tma_load_2d(asmem->k[warp], kvmap, 0, krow0 + (page * P.kv.n_kv_heads + kvh) * 64, &ms->att_bar[warp]);
-        tma_load_2d(asmem->v[warp], kvmap, 0, vrow0 + (page * P.kv.n_kv_heads + kvh) * 64, &ms->att_bar[warp]);
-      };
-      // the pages do not depend on this layer's projections (the new row is patched in below): fetch the first round now
-      csync();   // the union region is ours (previous phase of this CTA is through with it)
-      if (warp < kAttWarps && lane == 0 && p0 + warp < p1) issue_page(p0 + warp);
+      if (!att_separate) {
+        // the pages do not depend on this layer's projections (the new row is patched in below): fetch the first round now
+        csync();   // the union region is ours (previous phase of this CTA is through with it)
+        if (warp < AW && p0 + warp < p1) issue_page(l, p0 + warp, p0, true);
+      }
       pm(21);
       // prologue: fold the qkv slices (slice order) + bias, RoPE; q of the group -> shared; new K/V row
       const float* bias = P.bqkv[l];
@@ -603,27 +681,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         }
         a.x += bia.x, a.y += bia.y;
         if (which == 2) {
-          asmem->vnew[2 * i] = a.x, asmem->vnew[2 * i + 1] = a.y;
+          att_vnew[2 * i] = a.x, att_vnew[2 * i + 1] = a.y;
         } else {
           const float lo = a.x * cs - a.y * sn, hi = a.y * cs + a.x * sn;   // rows (2i, 2i+1) = dims (i, i + 32)
-          if (which == 0) asmem->q[idx >> 5][i] = lo, asmem->q[idx >> 5][i + 32] = hi;
-          else asmem->knew[i] = lo, asmem->knew[i + 32] = hi;
+          if (which == 0) att_q[(idx >> 5) * 64 + i] = lo, att_q[(idx >> 5) * 64 + i + 32] = hi;
+          else att_knew[i] = lo, att_knew[i + 32] = hi;
         }
       }
       pm(22);
       csync();
       if (appends && tid >= 128 && tid < 192) {  // the new token's K/V row joins the cache (bf16) for the steps to come
         const int d = tid - 128;
-        const int page = __ldcg(P.kv.page_table + b * P.kv.max_pages_per_seq + (pos >> 6));
-        P.kv.page_ptr(l, 0, page, kvh)[(pos & 63) * 64 + d] = __float2bfloat16(asmem->knew[d]);
-        P.kv.page_ptr(l, 1, page, kvh)[(pos & 63) * 64 + d] = __float2bfloat16(asmem->vnew[d]);
+        const int page = page_of(pos >> 6, p0);
+        P.kv.page_ptr(l, 0, page, kvh)[(pos & 63) * 64 + d] = __float2bfloat16(att_knew[d]);
+        P.kv.page_ptr(l, 1, page, kvh)[(pos & 63) * 64 + d] = __float2bfloat16(att_vnew[d]);
       }
-      if (warp < kAttWarps) {
+      if (warp < AW) {
         const int g = lane >> 2, t = lane & 3, lrow = lane & 7, lmat = lane >> 3;
         // query fragments: row g = head g of the group (rows >= n_rep and rows 8..15 are zero); scale * log2(e) folded in
         uint32_t qa[4][4];
         {
-          const float* qp = asmem->q[min(g, n_rep - 1)];
+          const float* qp = att_q + min(g, n_rep - 1) * 64;
           const float sc = (g < n_rep) ? P.scale_log2 : 0.f;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -639,17 +717,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
 #pragma unroll
         for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
         float m0 = -INFINITY, l0 = 0.f;
-        const uint32_t kbase = smem_u32(asmem->k[warp]), vbase = smem_u32(asmem->v[warp]);
-        for (int pg = p0 + warp; pg < p1; pg += kAttWarps) {
+        const uint32_t kbase = smem_u32(att_k(warp)), vbase = smem_u32(att_v(warp));
+        for (int pg = p0 + warp; pg < p1; pg += AW) {
           mbar_wait(&ms->att_bar[warp], att_par);
           att_par ^= 1;
           if (warp == 0) pm(23);
           if (appends && pg == (pos >> 6)) {  // patch the staged page with the new row (the copy may predate our store)
             const int r = pos & 63;
-            uint8_t* kb8 = reinterpret_cast<uint8_t*>(asmem->k[warp]);
-            uint8_t* vb8 = reinterpret_cast<uint8_t*>(asmem->v[warp]);
-            *reinterpret_cast<uint32_t*>(chunk_elem(kb8, r, 2 * lane)) = pack_bf16x2(asmem->knew[2 * lane], asmem->knew[2 * lane + 1]);
-            *reinterpret_cast<uint32_t*>(chunk_elem(vb8, r, 2 * lane)) = pack_bf16x2(asmem->vnew[2 * lane], asmem->vnew[2 * lane + 1]);
+            uint8_t* kb8 = reinterpret_cast<uint8_t*>(att_k(warp));
+            uint8_t* vb8 = reinterpret_cast<uint8_t*>(att_v(warp));
+            *reinterpret_cast<uint32_t*>(chunk_elem(kb8, r, 2 * lane)) = pack_bf16x2(att_knew[2 * lane], att_knew[2 * lane + 1]);
+            *reinterpret_cast<uint32_t*>(chunk_elem(vb8, r, 2 * lane)) = pack_bf16x2(att_vnew[2 * lane], att_vnew[2 * lane + 1]);
             __syncwarp();
           }
           float sc[8][4];
@@ -703,14 +781,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
               mma_bf16_16816(o[nd + 1], pa[j], vb[2], vb[3]);
             }
           }
-          __syncwarp();  // all lanes are done with the buffers before lane 0 refills them
-          if (lane == 0 && pg + kAttWarps < p1) issue_page(pg + kAttWarps);
+          __syncwarp();  // all lanes are done with the buffers before they are refilled
+          if (pg + AW < p1) issue_page(l, pg + AW, p0, !att_separate);
         }
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1), l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         if (g < n_rep) {
 #pragma unroll
-          for (int n = 0; n < 8; ++n) *reinterpret_cast<float2*>(&asmem->o[warp][g][8 * n + 2 * t]) = make_float2(o[n][0], o[n][1]);
-          if (t == 0) asmem->ml[warp][g][0] = m0, asmem->ml[warp][g][1] = l0;
+          for (int n = 0; n < 8; ++n) *reinterpret_cast<float2*>(att_o + (warp * 8 + g) * 64 + 8 * n + 2 * t) = make_float2(o[n][0], o[n][1]);
+          if (t == 0) att_ml[(warp * 8 + g) * 2] = m0, att_ml[(warp * 8 + g) * 2 + 1] = l0;
         }
       }
       csync();
@@ -719,13 +797,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         const int h = i >> 6, d = i & 63;
         float M = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < kAttWarps; ++w) M = fmaxf(M, asmem->ml[w][h][0]);
+        for (int w = 0; w < kAttWarpsMax; ++w)
+          if (w < AW) M = fmaxf(M, att_ml[(w * 8 + h) * 2]);
         float Ls = 0.f, O = 0.f;
 #pragma unroll
-        for (int w = 0; w < kAttWarps; ++w) {
-          const float wgt = exp2f(asmem->ml[w][h][0] - M);   // 0 for a warp that walked no page (m = -inf, l = 0)
-          Ls += wgt * asmem->ml[w][h][1];
-          O += wgt * asmem->o[w][h][d];
+        for (int w = 0; w < kAttWarpsMax; ++w) {
+          if (w < AW) {
+            const float wgt = exp2f(att_ml[(w * 8 + h) * 2] - M);   // 0 for a warp that walked no page (m = -inf, l = 0)
+            Ls += wgt * att_ml[(w * 8 + h) * 2 + 1];
+            O += wgt * att_o[(w * 8 + h) * 64 + d];
+          }
         }
         const long long hh = static_cast<long long>(b) * P.n_heads + kvh * n_rep + h;
         P.ao2[(hh * P.max_splits + my_split) * 64 + d] = make_float2(O, sf);
@@ -795,13 +876,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       const int per = B * 32;
       for (int e = tid; e < nch * per; e += kConsumerThreads) {
         const int c = e / per, r = e - c * per, b = r >> 5, k = (r & 31) * 2;
-        const float2* p = P.act2 + static_cast<long long>(b) * I + ms->ckb[kPhD][c] * 64 + k;
+        const int kbd = ms->ckb[kPhD][c];
         float4 t;
-        uint32_t spins = 0;
-        for (;;) {
-          t = ldp2(p);
-          if (__float_as_int(t.y) == stamp && __float_as_int(t.w) == stamp) break;
-          tc_spin_check(spins, "SwiGLU outputs");
+        if (plan.gu_split) {
+          // flat plan: activations j, j + 1 = gate/up rows 2j .. 2j + 3 of tile kbd; fold its K slices (slice order), then SwiGLU
+          const int nsl = __ldg(P.gu_nsl + kbd);
+          const float2* p = P.pg2 + static_cast<long long>(b) * 2 * I + 2 * (kbd * 64 + k);
+          const long long sstride = static_cast<long long>(B) * 2 * I;
+          float4 u0[kTcMaxGuSlices], u1[kTcMaxGuSlices];
+          uint32_t spins = 0;
+          for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int sl = 0; sl < kTcMaxGuSlices; ++sl)
+              if (sl < nsl) u0[sl] = ldp2(p + sl * sstride), u1[sl] = ldp2(p + sl * sstride + 2);
+#pragma unroll
+            for (int sl = 0; sl < kTcMaxGuSlices; ++sl)
+              if (sl < nsl)
+                ok = ok && __float_as_int(u0[sl].y) == stamp && __float_as_int(u0[sl].w) == stamp && __float_as_int(u1[sl].y) == stamp &&
+                     __float_as_int(u1[sl].w) == stamp;
+            if (ok) break;
+            tc_spin_check(spins, "gate/up slices");
+          }
+          float g0 = 0.f, up0 = 0.f, g1 = 0.f, up1 = 0.f;
+#pragma unroll
+          for (int sl = 0; sl < kTcMaxGuSlices; ++sl)
+            if (sl < nsl) g0 += u0[sl].x, up0 += u0[sl].z, g1 += u1[sl].x, up1 += u1[sl].z;
+          t.x = silu(g0) * up0, t.z = silu(g1) * up1;
+        } else {
+          const float2* p = P.act2 + static_cast<long long>(b) * I + kbd * 64 + k;
+          uint32_t spins = 0;
+          for (;;) {
+            t = ldp2(p);
+            if (__float_as_int(t.y) == stamp && __float_as_int(t.w) == stamp) break;
+            tc_spin_check(spins, "SwiGLU outputs");
+          }
         }
         __nv_bfloat16 h0, l0, h1, l1;
         split_hilo(t.x, h0, l0);
@@ -899,13 +1008,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       const float inv_t = 1.0f / P.samp.sp.temperature;
       const bool mask_eos = ms->mask_eos[b] != 0;
       const int eos = P.samp.sp.eos_id;
+      pm(120);
       for (int i = tid; i < nt; i += kConsumerThreads) keys[i] = f2key(__ldcg(P.tmax + static_cast<long long>(b) * nt + i));
       if (tid < 64) tiles[tid] = -1, counts[tid] = 0;
       csync();
       const int k = min(min(P.samp.sp.top_k, kTopKeep), nt);
       uint32_t thr;
       int take_eq;
+      pm(121);
       radix_select_kth(keys, nt, k, scratch, thr, take_eq, csync);
+      pm(122);
       // fewer tiles than top_k: the tile maxima bound nothing, every logit of every tile is a candidate
       const uint32_t cthr = nt < P.samp.sp.top_k ? 1u : thr;
       // the k tiles: maxima above the threshold, then the first take_eq tiles (index order) that equal it
@@ -927,6 +1039,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         kk[2] = (r0 + 2 < V) ? processed_key(x.z, r0 + 2, mask_eos, eos, inv_t) : 0u;
         kk[3] = (r0 + 3 < V) ? processed_key(x.w, r0 + 3, mask_eos, eos, inv_t) : 0u;
       };
+      // ---- fast path: the candidates (key >= threshold) of the chosen tiles go straight into shared memory; all loads
+      //      of a warp's tiles are in flight together (one round trip to L2), the exact top-k is a rank sort.
+      const bool stateless = false;
+      const int ngen = __ldcg(P.samp.n_generated + b);
+      const bool is_done = __ldcg(P.samp.done + b) != 0;
+      float2* h2dst = fold_cta ? P.h2 + (static_cast<long long>(fold_no & 1) * B + b) * H : nullptr;
+      const float h2stamp = __int_as_float(P.hstamp_base + fold_no);
+      constexpr int kFastCap = 512;
+      Cand* fc = reinterpret_cast<Cand*>(keys + ((nt + 3) & ~3));
+      int* fcnt = &ms->sel[1];
+      const bool fast_fits = key_cap >= ((nt + 3) & ~3) + 2 * kFastCap;
+      if (tid == 0) *fcnt = 0;
+      csync();
+      if (fast_fits) {
+        constexpr int kPerWarp = (kTopKeep + kConsumerWarps - 1) / kConsumerWarps;
+        uint32_t kk[kPerWarp][4];
+#pragma unroll
+        for (int u = 0; u < kPerWarp; ++u) {
+          const int j = warp + u * kConsumerWarps;
+          if (j < k) tile_keys(tiles[j], kk[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kPerWarp; ++u) {
+          const int j = warp + u * kConsumerWarps;
+          if (j < k) {
+            const int tile = tiles[j];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const bool hit = kk[u][q] >= cthr && kk[u][q] != 0u;
+              const uint32_t m = __ballot_sync(0xffffffffu, hit);
+              if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(fcnt, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int o = base + __popc(m & ((1u << lane) - 1u));
+                if (hit && o < kFastCap) fc[o].v = key2f(kk[u][q]), fc[o].i = tile * 128 + lane * 4 + q;
+              }
+            }
+          }
+        }
+      }
+      csync();
+      pm(123);
+      const int nc = fast_fits ? *fcnt : kFastCap + 1;
+      if (nc <= kFastCap) {
+        const int k2 = min(min(P.samp.sp.top_k, kTopKeep), nc);
+        for (int i = tid; i < nc; i += kConsumerThreads) {   // rank among the candidates: (score desc, index asc) is a total order
+          const Cand me = fc[i];
+          int rank = 0;
+          for (int j = 0; j < nc; ++j) rank += cand_before(fc[j], me) ? 1 : 0;
+          if (rank < k2) win[rank] = me;
+        }
+        csync();
+        pm(124);
+        sample_finish(P.samp, b, k2, win, s_tok, stateless, ngen, is_done, csync, h2dst, h2stamp);
+        pm(125);
+        return;
+      }
+      // ---- general path (thousands of candidates: tiny vocabularies, or exact ties at the threshold)
       // pass 1: candidates (key >= threshold) per chosen tile
       for (int j = warp; j < k; j += kConsumerWarps) {
         uint32_t kk[4];
@@ -978,11 +1149,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       }
       csync();
       sample_stage2_seq(P.samp, b, ncand, keys, scratch, win, s_tok, csync, NoMark(), kCandPitch);
-      if (fold_cta) {  // the next token's embedding becomes the residual stream of the next step's first fold
+      if (h2dst) {  // the next token's embedding becomes the residual stream of the next step's first fold
         csync();
-        float2* hdst = P.h2 + (static_cast<long long>(fold_no & 1) * B + b) * H;
-        const float sf = __int_as_float(P.hstamp_base + fold_no);
-        for (int i = tid; i < H; i += kConsumerThreads) hdst[i] = make_float2(P.h[static_cast<long long>(b) * H + i], sf);
+        for (int i = tid; i < H; i += kConsumerThreads) h2dst[i] = make_float2(P.h[static_cast<long long>(b) * H + i], h2stamp);
       }
     };
 
@@ -1009,11 +1178,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         ms->mask_eos[tid] = __ldcg(P.samp.n_generated + tid) < P.samp.sp.min_new_tokens ? 1 : 0;
       }
       csync();
+      cache_pages();
+      fence_proxy_async_all();   // KV rows appended in earlier steps (generic proxy, behind grid barriers) -> this step's TMA reads
+      csync();
       if (fold_cta) {
         // ---------------- batch <= 4: no grid barrier inside the layers, every hand-off is polled
         for (int l = 0; l < L; ++l) {
           const int st = stamp_of(step, l);
           prof.fine = prof.buf != nullptr && l == 2;
+          attn_prefetch(l);
           if (plan.n[kPhQ] > 0) fold_stage(P.pd2, l > 0 ? P.sd : 0, stamp_of(step, l - 1), H, P.ln1[l], kPhQ, plan.fold_q != 0);
           else ++fold_no;
           epi_partials(kPhQ, P.pq2, P.qkv_n, st);
@@ -1023,9 +1196,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
           if (plan.n[kPhO] > 0) stage_attn(st);
           epi_partials(kPhO, P.po2, H, st);
           if (tid == 0) prof.mark(102);
-          if (plan.n[kPhG] > 0) fold_stage(P.po2, P.so, st, H, P.ln2[l], -1, plan.fold_g != 0);
+          if (plan.n[kPhG] > 0) fold_stage(P.po2, P.so, st, H, P.ln2[l], plan.gu_split ? kPhG : -1, plan.fold_g != 0);
           else ++fold_no;
-          epi_swiglu(st);
+          if (plan.gu_split) epi_partials(kPhG, P.pg2, 2 * I, st);
+          else epi_swiglu(st);
           if (tid == 0) prof.mark(103);
           if (plan.n[kPhD] > 0) stage_act(st);
           epi_partials(kPhD, P.pd2, H, st);
@@ -1040,23 +1214,32 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         else grid_sync([&] { load_bop_full(xmap, n_head_tiles > 0); });
         for (int l = 0; l < L; ++l) {
           const int st = stamp_of(step, l);
+          prof.fine = prof.buf != nullptr && l == 2;
           epi_partials(kPhQ, P.pq2, P.qkv_n, st);
+          if (tid == 0) prof.mark(100);
           attention_phase(l, st);
+          if (tid == 0) prof.mark(101);
           if (plan.n[kPhO] > 0) stage_attn(st);
           epi_partials(kPhO, P.po2, H, st);
+          if (tid == 0) prof.mark(102);
           fold_phase(P.po2, P.so, st, H, P.ln2[l]);
+          if (tid == 0) prof.mark(105);
           grid_sync([&] { load_bop_full(xmap, plan.n[kPhG] > 0); });
           epi_swiglu(st);
+          if (tid == 0) prof.mark(103);
           grid_sync([&] { load_bop_split(amap, kPhD); });
           epi_partials(kPhD, P.pd2, H, st);
+          if (tid == 0) prof.mark(104);
           const bool last = l + 1 == L;
           fold_phase(P.pd2, P.sd, st, H, last ? P.final_norm : P.ln1[l + 1]);
+          if (tid == 0) prof.mark(106);
           if (last) grid_sync([&] { load_bop_full(xmap, n_head_tiles > 0); });
           else grid_sync([&] { load_bop_split(xmap, kPhQ); });
         }
       }
       // ---- lm_head
       epi_head();
+      if (tid == 0) prof.mark(110);
       grid_sync(no_post);
       // ---- sampler (+ tests: keep every step's logits)
       if (P.logits_out) {
@@ -1065,7 +1248,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         for (long long i = static_cast<long long>(blockIdx.x) * kConsumerThreads + tid; i < n; i += static_cast<long long>(G) * kConsumerThreads)
           dst[i] = __ldcg(P.logits + i);
       }
+      prof.fine = prof.buf != nullptr;
       sample_phase();
+      if (tid == 0) prof.mark(111);
       grid_sync(no_post);
       bool all_done = true;
       for (int b = 0; b < B; ++b) all_done = all_done && (__ldcg(P.samp.done + b) != 0);
@@ -1081,54 +1266,81 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static size_t tc_union_bytes(int nt) {
-  size_t u = size_t(14) * nt * 128 + (nt == 16 ? 20 * 1024 : 0);   // B chunks (+ fold_in_cta: fp32 rows and the norm weights)
-  const size_t att = (sizeof(TcAttnSmem) + 1023) & ~size_t(1023);
-  return u > att ? u : att;
+static size_t tc_chunk_bytes(int nt) {   // B chunks (+ fold_in_cta: fp32 rows and the norm weights), 1024-aligned
+  const size_t u = size_t(14) * nt * 128 + (nt == 16 ? 20 * 1024 : 0);
+  return (u + 1023) & ~size_t(1023);
+}
+static size_t tc_attn_bytes(int aw) { return (tc_attn_layout_bytes(aw) + 1023) & ~size_t(1023); }
+
+bool tc_fold_in_cta(int B, int hidden) {
+  const char* fe = getenv("NT_TC_FOLD");   // experiments: "phase" forces the fold phases at small batch
+  return B <= 4 && size_t(B) * hidden * 4 <= 16 * 1024 && hidden <= 1024 && !(fe && fe[0] == 'p');
 }
 
-size_t tc_smem_bytes(int nt) {
-  const size_t budget = 227 * 1024;
-  const size_t misc = (sizeof(TcMisc) + 127) & ~size_t(127);
-  const size_t fixed = tc_union_bytes(nt) + misc + 1024;
-  const int ns = int((budget - fixed) / 16384);
-  return size_t(ns > 16 ? 16 : ns) * 16384 + fixed;
-}
-
-int tc_build_plan(const TcShape& s, int G, TcPlan* plan, int* sq, int* so, int* sd, int* ntiles, int* max_split_chunks) {
+int tc_build_plan(const TcShape& s, int G, bool flat, TcPlan* plan, unsigned char* gu_nsl, TcPlanInfo* info) {
   if (G < 8 || G > 256) return set_error(NT_ERR_INVALID, "decode_tc: %d SMs unsupported", G);
   if (s.hidden % 64 || s.inter % 64) return set_error(NT_ERR_INVALID, "decode_tc: hidden / inter must be multiples of 64");
   const int Tq = (s.qkv_n + 127) / 128, To = (s.hidden + 127) / 128, Tg = (2 * s.inter + 127) / 128;
   const int KBh = s.hidden / 64, KBo = s.n_heads, KBi = s.inter / 64;
   if (KBh > 14) return set_error(NT_ERR_INVALID, "decode_tc: hidden %d > 896 does not fit the shared-memory plan", s.hidden);
   for (int c = 0; c < G; ++c) plan[c] = TcPlan{};
-  // gate/up keeps K whole: its row tiles go to a dedicated, evenly spread subset of the CTAs
-  int ngu = Tg < G ? Tg : G;
-  std::vector<int> gu, rest;
-  if (G - ngu < 16) {  // too few CTAs would be left for the split phases: everybody does everything
-    for (int c = 0; c < G; ++c) gu.push_back(c), rest.push_back(c);
-    ngu = G;
-  } else {
-    for (int c = 0; c < G; ++c) {
-      const bool is_gu = ((c + 1) * ngu) / G > (c * ngu) / G;
-      (is_gu ? gu : rest).push_back(c);
-    }
-  }
   auto add = [&](int cta, int ph, TcItem it) -> bool {
     TcPlan& p = plan[cta];
     if (p.n[ph] >= kTcMaxItems) return false;
     p.it[ph][p.n[ph]++] = it;
     return true;
   };
-  for (int t = 0; t < Tg; ++t)
-    if (!add(gu[t % gu.size()], kPhG, TcItem{short(t), 0, short(KBh), 0})) return set_error(NT_ERR_INVALID, "decode_tc: too many gate/up tiles per CTA");
+  std::vector<int> rest;
+  int sg = 1;
+  if (flat) {
+    // gate/up as (tile, k-block) units in tile-major order: CTA c owns units [U c / G, U (c + 1) / G)
+    const int U = Tg * KBh;
+    std::vector<int> nsl(Tg, 0);
+    for (int c = 0; c < G; ++c) {
+      int u0 = int((static_cast<long long>(U) * c) / G);
+      const int u1 = int((static_cast<long long>(U) * (c + 1)) / G);
+      while (u0 < u1) {
+        const int t = u0 / KBh, kb0 = u0 % KBh;
+        const int n = (u1 - u0 < KBh - kb0) ? (u1 - u0) : (KBh - kb0);
+        if (nsl[t] >= kTcMaxGuSlices || !add(c, kPhG, TcItem{short(t), short(kb0), short(n), short(nsl[t])}))
+          return set_error(NT_ERR_INVALID, "decode_tc: flat gate/up plan does not fit");
+        ++nsl[t];
+        u0 += n;
+      }
+      plan[c].gu_split = 1;
+    }
+    for (int t = 0; t < Tg; ++t) {
+      if (gu_nsl) gu_nsl[t] = static_cast<unsigned char>(nsl[t]);
+      if (nsl[t] > sg) sg = nsl[t];
+    }
+    for (int c = 0; c < G; ++c) rest.push_back(c);
+  } else {
+    // gate/up keeps K whole (its SwiGLU epilogue is not linear): its row tiles go to a dedicated, evenly spread subset
+    int ngu = Tg < G ? Tg : G;
+    std::vector<int> gu;
+    if (G - ngu < 16) {  // too few CTAs would be left for the split phases: everybody does everything
+      for (int c = 0; c < G; ++c) gu.push_back(c), rest.push_back(c);
+    } else {
+      for (int c = 0; c < G; ++c) {
+        const bool is_gu = ((c + 1) * ngu) / G > (c * ngu) / G;
+        (is_gu ? gu : rest).push_back(c);
+      }
+    }
+    for (int t = 0; t < Tg; ++t)
+      if (!add(gu[t % gu.size()], kPhG, TcItem{short(t), 0, short(KBh), 0})) return set_error(NT_ERR_INVALID, "decode_tc: too many gate/up tiles per CTA");
+  }
   const int nr = int(rest.size());
   int rot = 0;
+  int ov[3] = {0, 0, 0};   // NT_TC_SLICES="q,o,d": K slices per phase (experiments; 0 = automatic)
+  if (const char* e = getenv("NT_TC_SLICES")) sscanf(e, "%d,%d,%d", &ov[0], &ov[1], &ov[2]);
   auto split_phase = [&](int ph, int T, int KB, int* slices) -> bool {
     int S = nr / T;
+    const int want = ph == kPhQ ? ov[0] : (ph == kPhO ? ov[1] : ov[2]);
+    if (want > 0) S = want;
     if (S < 1) S = 1;
     if (S > KB) S = KB;
     if (S > kTcMaxSlices) S = kTcMaxSlices;
+    while ((KB + S - 1) / S > 14) ++S;   // an item's k-blocks must fit the staging area
     *slices = S;
     for (int t = 0; t < T; ++t)
       for (int z = 0; z < S; ++z) {
@@ -1138,12 +1350,13 @@ int tc_build_plan(const TcShape& s, int G, TcPlan* plan, int* sq, int* so, int* 
       }
     return true;
   };
-  if (!split_phase(kPhQ, Tq, KBh, sq) || !split_phase(kPhO, To, KBo, so) || !split_phase(kPhD, To, KBi, sd))
+  if (!split_phase(kPhQ, Tq, KBh, &info->sq) || !split_phase(kPhO, To, KBo, &info->so) || !split_phase(kPhD, To, KBi, &info->sd))
     return set_error(NT_ERR_INVALID, "decode_tc: too many split-K items per CTA");
   int worst = 0;
   bool fq = false, fg = false;
   for (int c = 0; c < G; ++c) {
-    for (int ph : {kPhQ, kPhO, kPhD}) {
+    for (int ph = 0; ph < 4; ++ph) {
+      if (ph == kPhG && !flat) continue;
       int chunks = 0;
       for (int i = 0; i < plan[c].n[ph]; ++i) chunks += plan[c].it[ph][i].nkb;
       if (chunks > worst) worst = chunks;
@@ -1151,9 +1364,12 @@ int tc_build_plan(const TcShape& s, int G, TcPlan* plan, int* sq, int* so, int* 
     if (!fq && plan[c].n[kPhQ] > 0) plan[c].fold_q = 1, fq = true;
     if (!fg && plan[c].n[kPhG] > 0) plan[c].fold_g = 1, fg = true;
   }
-  *max_split_chunks = worst;
+  if (worst > 14) return set_error(NT_ERR_INVALID, "decode_tc: %d k-blocks per CTA exceed the staging area", worst);
+  info->max_chunks = worst;
+  info->sg = sg;
+  info->gu_split = flat ? 1 : 0;
   const int nt = (s.vocab + 127) / 128;
-  *ntiles = nt;
+  info->ntiles = nt;
   for (int c = 0; c < G; ++c) {
     plan[c].head_t0 = int((static_cast<long long>(nt) * c) / G);
     plan[c].head_t1 = int((static_cast<long long>(nt) * (c + 1)) / G);
@@ -1164,11 +1380,23 @@ int tc_build_plan(const TcShape& s, int G, TcPlan* plan, int* sq, int* so, int* 
 template <int NT, bool HILO>
 static int launch_tc(TcParams& P, int num_sms, cudaStream_t stream) {
   auto kern = decode_tc_kernel<NT, HILO>;
-  const size_t smem = tc_smem_bytes(NT);
+  const size_t budget = 227 * 1024;
   const size_t misc = (sizeof(TcMisc) + 127) & ~size_t(127);
-  P.nstages = int((smem - tc_union_bytes(NT) - misc - 1024) / 16384);
-  P.uni_off = unsigned(size_t(P.nstages) * 16384);
-  P.uni_bytes = unsigned(tc_union_bytes(NT));
+  // batch <= 4: the attention staging sits BEHIND the B chunks, so a layer's KV pages are fetched while the qkv
+  // projection still runs; otherwise the two alias (a phase uses one or the other)
+  const bool separate = P.fold_in_cta != 0 && !getenv("NT_TC_NO_PREFETCH");
+  // dedicated staging: two page-walking warps (a split is 1..4 pages at batch <= 4), which leaves the weight ring 8 stages
+  P.att_warps = separate ? 2 : 4;
+  const size_t chunks = tc_chunk_bytes(NT), att = tc_attn_bytes(P.att_warps);
+  const size_t uni = separate ? chunks + att : (chunks > att ? chunks : att);
+  int ns = int((budget - uni - misc - 1024) / 16384);
+  if (ns > 16) ns = 16;
+  if (ns < 3) return set_error(NT_ERR_INVALID, "decode_tc: shared memory plan leaves %d ring stages", ns);
+  const size_t smem = size_t(ns) * 16384 + uni + misc + 1024;
+  P.nstages = ns;
+  P.uni_off = unsigned(size_t(ns) * 16384);
+  P.uni_bytes = unsigned(uni);
+  P.att_off = P.uni_off + (separate ? unsigned(chunks) : 0u);
   P.misc_off = P.uni_off + P.uni_bytes;
   NT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
   int per_sm = 0;
@@ -1182,7 +1410,7 @@ static int launch_tc(TcParams& P, int num_sms, cudaStream_t stream) {
   return NT_OK;
 }
 
-int launch_decode_tc(TcParams& P, int B, int num_sms, int max_split_chunks, cudaStream_t stream) {
+int launch_decode_tc(TcParams& P, int B, int num_sms, const TcPlanInfo& info, cudaStream_t stream) {
   if (B < 1 || B > kTcMaxBatch) return set_error(NT_ERR_INVALID, "decode_tc: batch %d not in 1..%d", B, kTcMaxBatch);
   if (P.n_heads % P.n_kv || P.n_heads / P.n_kv > 8) return set_error(NT_ERR_INVALID, "decode_tc: unsupported GQA ratio");
   P.B = B;
@@ -1193,11 +1421,10 @@ int launch_decode_tc(TcParams& P, int B, int num_sms, int max_split_chunks, cuda
   if (cap > P.max_splits) cap = P.max_splits;
   P.split_cap = cap;
   const int nt = B <= 16 ? 16 : (B <= 32 ? 32 : 64);
-  if (max_split_chunks > 14) return set_error(NT_ERR_INVALID, "decode_tc: %d k-blocks per CTA exceed the staging area", max_split_chunks);
-  if (sizeof(TcAttnSmem) > tc_union_bytes(nt)) return set_error(NT_ERR_INVALID, "decode_tc: attention staging does not fit");
+  if (info.max_chunks > 14) return set_error(NT_ERR_INVALID, "decode_tc: %d k-blocks per CTA exceed the staging area", info.max_chunks);
+  P.fold_in_cta = tc_fold_in_cta(B, P.hidden) ? 1 : 0;
+  if (info.gu_split && !P.fold_in_cta) return set_error(NT_ERR_INVALID, "decode_tc: the flat plan needs the in-CTA fold (batch <= 4)");
   const bool hilo = B <= 8;
-  const char* fe = getenv("NT_TC_FOLD");   // experiments: "phase" forces the fold phases at small batch
-  P.fold_in_cta = (B <= 4 && size_t(B) * P.hidden * 4 <= 16 * 1024 && P.hidden <= 1024 && !(fe && fe[0] == 'p')) ? 1 : 0;
   if (hilo) return launch_tc<16, true>(P, num_sms, stream);
   if (nt == 16) return launch_tc<16, false>(P, num_sms, stream);
   if (nt == 32) return launch_tc<32, false>(P, num_sms, stream);

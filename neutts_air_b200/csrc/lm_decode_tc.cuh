@@ -11,6 +11,7 @@ constexpr int kTcMaxItems = 4;      // work items of one GEMM phase a CTA may ow
 constexpr int kTcThreads = 320;     // 8 worker warps + 1 weight-stream warp + 1 MMA warp
 constexpr int kTcMaxBatch = 64;
 constexpr int kTcMaxSlices = 16;
+constexpr int kTcMaxGuSlices = 4;   // K slices of one gate/up tile in the flat plan (batch <= 4)
 
 // One GEMM work item: rows [tile*128, tile*128+128) of a weight matrix times k-blocks [kb0, kb0+nkb) of the
 // activations (a k-block = 64 elements = one 128-byte swizzle row).  Items of the split-K phases (qkv, o, down)
@@ -26,6 +27,14 @@ struct TcPlan {
   TcItem it[4][kTcMaxItems];
   int head_t0, head_t1;           // lm_head row tiles [t0, t1)
   int fold_q, fold_g;             // batch <= 4: this CTA writes the folded residual stream back (one CTA per fold point)
+  int gu_split;                   // 1: gate/up items carry their own K range and write raw partial sums (flat plan)
+};
+
+struct TcPlanInfo {               // what the host needs to know about a plan
+  int sq, so, sd, sg;             // K slices per phase (sg: most slices any gate/up tile has; 1 = whole K)
+  int ntiles;                     // lm_head row tiles
+  int max_chunks;                 // most B-operand k-blocks a CTA stages in one phase
+  int gu_split;
 };
 
 struct TcParams {
@@ -51,7 +60,9 @@ struct TcParams {
   float2 *pq2, *po2, *pd2;        // split-K partial sums [slice][B][rows]
   int sq, so, sd;                 // slices per phase
   float2 *ao2, *aml2;             // split-KV attention partials [B][n_heads][max_splits][64] / [..][2] = ((m, .), (l, .))
-  float2* act2;                   // batch <= 4: SwiGLU output [B][inter] (fp32 value, stamp)
+  float2* act2;                   // batch <= 4, whole-K gate/up: SwiGLU output [B][inter] (fp32 value, stamp)
+  float2* pg2;                    // batch <= 4, flat plan: gate/up partial sums [slice][B][2 * inter]
+  const unsigned char* gu_nsl;    // flat plan: K slices of every gate/up tile (device, [tiles])
   float2* h2;                     // batch <= 4: residual stream, ping-pong [2][B][hidden]
   int stamp_base, hstamp_base;    // stamps of this launch lie above these (host counters)
   int max_splits, split_cap;
@@ -69,15 +80,19 @@ struct TcParams {
   // shared-memory plan
   int nstages;
   unsigned uni_off, uni_bytes, misc_off;
+  int att_warps;                  // page-walking warps of the attention phase (2 | 4)
+  unsigned att_off;               // attention staging: inside the union region (aliased) or behind it (batch <= 4: pages prefetched)
   int fold_in_cta;                // 1: batch <= 4, consumers fold the split-K slices themselves (no fold phases)
 };
 
 struct TcShape {  // everything the planner needs
   int hidden, inter, n_heads, n_kv, qkv_n, vocab;
 };
-// Returns NT_OK and fills plan[G], slices and tile count; NT_ERR_INVALID when the shape does not fit the kernel.
-int tc_build_plan(const TcShape& s, int G, TcPlan* plan, int* sq, int* so, int* sd, int* ntiles, int* max_split_chunks);
-int launch_decode_tc(TcParams& P, int B, int num_sms, int max_split_chunks, cudaStream_t stream);
-size_t tc_smem_bytes(int nt);
+// Returns NT_OK and fills plan[G] (+ gu_nsl[tiles of gate/up] for the flat plan) and info; NT_ERR_INVALID when the
+// shape does not fit the kernel.  flat: gate/up is cut into equal (tile, k-block) ranges over ALL CTAs and its
+// SwiGLU moves into the down_proj staging (batch <= 4 only: larger batches hand the activations over by TMA).
+int tc_build_plan(const TcShape& s, int G, bool flat, TcPlan* plan, unsigned char* gu_nsl, TcPlanInfo* info);
+bool tc_fold_in_cta(int B, int hidden);
+int launch_decode_tc(TcParams& P, int B, int num_sms, const TcPlanInfo& info, cudaStream_t stream);
 
 }  // namespace nt

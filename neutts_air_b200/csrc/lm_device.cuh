@@ -691,6 +691,77 @@ NT_DEVINL void sample_stage1_chunk(const SamplerParams& p, int b, int chunk, uin
   emit_local_topk(p, keys, n, base, (static_cast<long long>(b) * p.nchunks + chunk) * kTopKeep, scratch, sync);
 }
 
+// Tail of the sampler for sequence b, given the k kept candidates sorted (score desc, index asc) in win[0..k):
+// softmax over them (TopK processor + softmax, utils.py:2789), Philox draw, state update, stop flags, and the next
+// token's embedding -> residual stream row (fp32; optionally also as (value, stamp) pairs for the polled hand-off).
+// Clobbers win[kTopKeep .. 2 kTopKeep) (exponentials).
+template <typename Sync>
+NT_DEVINL void sample_finish(const SamplerParams& p, int b, int k, Cand* win, int* s_tok, bool stateless, int ngen, bool is_done, Sync sync,
+                             float2* h2dst = nullptr, float h2stamp = 0.f) {
+  const int tid = threadIdx.x;
+  float* ev = reinterpret_cast<float*>(win + kTopKeep);   // [kTopKeep] exp(score - max)
+  if (tid < 32) {
+    const float m = win[0].v;
+    const float e0 = (tid < k) ? __expf(win[tid].v - m) : 0.f;
+    const float e1 = (tid + 32 < k) ? __expf(win[tid + 32].v - m) : 0.f;
+    const float sum = warp_sum(e0 + e1);
+    if (p.dbg_topk_val) {
+      p.dbg_topk_val[b * kTopKeep + tid] = (tid < k) ? e0 / sum : 0.f;
+      p.dbg_topk_val[b * kTopKeep + tid + 32] = (tid + 32 < k) ? e1 / sum : 0.f;
+      p.dbg_topk_idx[b * kTopKeep + tid] = (tid < k) ? win[tid].i : -1;
+      p.dbg_topk_idx[b * kTopKeep + tid + 32] = (tid + 32 < k) ? win[tid + 32].i : -1;
+    }
+    ev[tid] = e0, ev[tid + 32] = e1;
+    __syncwarp();
+    if (tid == 0) {
+      int tok;
+      if (p.sp.forced && !stateless) {
+        tok = p.sp.forced[static_cast<long long>(b) * p.max_new + ngen];
+      } else if (p.sp.greedy) {
+        tok = win[0].i;
+      } else {
+        uint32_t ctr[4] = {static_cast<uint32_t>(stateless ? p.step_override : ngen), static_cast<uint32_t>(b + p.slot_base), 0u, 0u};
+        philox4x32_10(ctr, static_cast<uint32_t>(p.sp.seed), static_cast<uint32_t>(p.sp.seed >> 32));
+        const float u = (ctr[0] >> 8) * (1.0f / 16777216.0f);  // [0,1)
+        const float target = u * sum;
+        float cum = 0.f;
+        tok = win[k - 1].i;
+        for (int j = 0; j < k; ++j) {   // sequential inverse CDF over the sorted candidates (multinomial semantics)
+          cum += ev[j];
+          if (cum > target) {
+            tok = win[j].i;
+            break;
+          }
+        }
+      }
+      *s_tok = tok;
+      if (p.dbg_token) p.dbg_token[b] = tok;
+      if (!stateless && !is_done) {
+        p.out_tokens[static_cast<long long>(b) * p.max_new + ngen] = tok;
+        p.n_generated[b] = ngen + 1;
+        p.cur_token[b] = tok;
+        const int cached = __ldcg(p.seq_lens + b) + p.advance;  // decode: this step's input token is now in the KV cache
+        if (p.advance) p.seq_lens[b] = cached;
+        const int total = cached + 1;  // tokens in context once `tok` is appended
+        const int lim = p.sp.limits ? min(p.sp.max_new_tokens, __ldg(p.sp.limits + b)) : p.sp.max_new_tokens;
+        if (tok == p.sp.eos_id || ngen + 1 >= lim || ngen + 1 >= p.max_new || total >= p.max_ctx) p.done[b] = 1;
+      }
+    }
+  }
+  sync();
+  if (!stateless && !is_done && p.h) {
+    const int tok = *s_tok;
+    const __nv_bfloat16* e = p.embed + static_cast<long long>(tok) * p.hidden;
+    for (int i = tid; i < p.hidden; i += kConsumerThreads) {
+      const float f = __bfloat162float(e[i]);
+      p.h[static_cast<long long>(b) * p.hidden + i] = f;
+      if (h2dst) h2dst[i] = make_float2(f, h2stamp);
+    }
+  } else if (h2dst) {   // finished sequence: the row keeps its value, but the next fold still waits for the stamp
+    for (int i = tid; i < p.hidden; i += kConsumerThreads) h2dst[i] = make_float2(p.h[static_cast<long long>(b) * p.hidden + i], h2stamp);
+  }
+}
+
 // Sampler stage 2 for sequence b: top-k of the candidate scores (already processed), softmax, draw,
 // state update, next embedding.  keys: [ncand] uint32 shared; scratch: [kSelScratch]; win: [2*kTopKeep].
 struct NoMark {
@@ -748,59 +819,7 @@ NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint3
   sync();
   mark();  // winners sorted
 
-  if (tid < 32) {
-    // softmax over the k kept scores (TopK processor + softmax, utils.py:2789)
-    const float m = win[0].v;
-    const float e0 = (tid < k) ? __expf(win[tid].v - m) : 0.f;
-    const float e1 = (tid + 32 < k) ? __expf(win[tid + 32].v - m) : 0.f;
-    const float sum = warp_sum(e0 + e1);
-    if (p.dbg_topk_val) {
-      p.dbg_topk_val[b * kTopKeep + tid] = (tid < k) ? e0 / sum : 0.f;
-      p.dbg_topk_val[b * kTopKeep + tid + 32] = (tid + 32 < k) ? e1 / sum : 0.f;
-      p.dbg_topk_idx[b * kTopKeep + tid] = (tid < k) ? win[tid].i : -1;
-      p.dbg_topk_idx[b * kTopKeep + tid + 32] = (tid + 32 < k) ? win[tid + 32].i : -1;
-    }
-    if (tid == 0) {
-      int tok;
-      if (p.sp.forced && !stateless) {
-        tok = p.sp.forced[static_cast<long long>(b) * p.max_new + ngen];
-      } else if (p.sp.greedy) {
-        tok = win[0].i;
-      } else {
-        uint32_t ctr[4] = {static_cast<uint32_t>(stateless ? p.step_override : ngen), static_cast<uint32_t>(b + p.slot_base), 0u, 0u};
-        philox4x32_10(ctr, static_cast<uint32_t>(p.sp.seed), static_cast<uint32_t>(p.sp.seed >> 32));
-        const float u = (ctr[0] >> 8) * (1.0f / 16777216.0f);  // [0,1)
-        const float target = u * sum;
-        float cum = 0.f;
-        tok = win[k - 1].i;
-        for (int j = 0; j < k; ++j) {
-          cum += __expf(win[j].v - m);
-          if (cum > target) {
-            tok = win[j].i;
-            break;
-          }
-        }
-      }
-      *s_tok = tok;
-      if (p.dbg_token) p.dbg_token[b] = tok;
-      if (!stateless && !is_done) {
-        p.out_tokens[static_cast<long long>(b) * p.max_new + ngen] = tok;
-        p.n_generated[b] = ngen + 1;
-        p.cur_token[b] = tok;
-        const int cached = __ldcg(p.seq_lens + b) + p.advance;  // decode: this step's input token is now in the KV cache
-        if (p.advance) p.seq_lens[b] = cached;
-        const int total = cached + 1;  // tokens in context once `tok` is appended
-        const int lim = p.sp.limits ? min(p.sp.max_new_tokens, __ldg(p.sp.limits + b)) : p.sp.max_new_tokens;
-        if (tok == p.sp.eos_id || ngen + 1 >= lim || ngen + 1 >= p.max_new || total >= p.max_ctx) p.done[b] = 1;
-      }
-    }
-  }
-  sync();
-  if (!stateless && !is_done && p.h) {
-    const int tok = *s_tok;
-    const __nv_bfloat16* e = p.embed + static_cast<long long>(tok) * p.hidden;
-    for (int i = tid; i < p.hidden; i += kConsumerThreads) p.h[static_cast<long long>(b) * p.hidden + i] = __bfloat162float(e[i]);
-  }
+  sample_finish(p, b, k, win, s_tok, stateless, ngen, is_done, sync);
 }
 
 }  // namespace nt

@@ -170,7 +170,9 @@ def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | Non
     ``mirror`` switches on the rounding points the CUDA path states in DESIGN.md, so
     the kernels can be checked to ~fp32 accuracy against their own specification (it is
     not part of the reference semantics; ``mirror=None`` is the reference):
-      "decode"  (GEMV path, batch <= 4): K/V rounded to bf16 when cached, all else fp32;
+      "decode"  (CUDA-core GEMV chain): K/V rounded to bf16 when cached, all else fp32;
+      "decode_tc" (persistent tcgen05 decode kernel, batch <= 8): as "decode" (activations travel as bf16 hi + lo
+                pairs, fp32-grade), but attention runs on bf16 tensor-core operands (scaled query, probabilities);
       "prefill" (tensor-core path): additionally the normalised activations, the
                 attention output and the SwiGLU output are rounded to bf16 (GEMM A operands), and
                 attention runs on bf16 tensor-core operands (scaled query and probabilities);
@@ -187,7 +189,7 @@ def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | Non
     pos = torch.arange(past, past + T)
     cos, sin = rope_cos_sin(pos, cfg.head_dim, cfg.rope_theta)
     n_rep = cfg.num_heads // cfg.num_kv_heads
-    assert mirror in (None, "decode", "prefill", "batched")
+    assert mirror in (None, "decode", "decode_tc", "prefill", "batched")
     kv_round_bf16 = mirror is not None
     rb = (lambda t: t.bfloat16().float()) if mirror in ("prefill", "batched") else (lambda t: t)
     rb_head = (lambda t: t.bfloat16().float()) if mirror == "batched" else (lambda t: t)
@@ -204,7 +206,7 @@ def forward(cfg: LMConfig, w: LMWeights, ids: torch.Tensor, cache: KVCache | Non
         if kv_round_bf16:
             k, v = k.bfloat16().float(), v.bfloat16().float()
         kk, vv = cache.update(li, k, v)                            # :225
-        a = attention(q, kk, vv, causal_offset=past, n_rep=n_rep, mma_bf16=(mirror in ("prefill", "batched")))  # :231
+        a = attention(q, kk, vv, causal_offset=past, n_rep=n_rep, mma_bf16=(mirror in ("prefill", "batched", "decode_tc")))  # :231
         a = rb(a.reshape(T, -1))
         h = h + a @ L["wo"].T                                      # :244, :302
         h_mid = h

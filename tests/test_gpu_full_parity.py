@@ -35,8 +35,8 @@ def full(cuda):
     return cfg, w
 
 
-def _tf(lm, prompts, forced, n_new):
-    sp = lm.sampling(EOS, min_new_tokens=0, max_new_tokens=n_new, forced=forced)
+def _tf(lm, prompts, forced, n_new, eos=EOS):
+    sp = lm.sampling(eos, min_new_tokens=0, max_new_tokens=n_new, forced=forced)
     l0 = lm.prefill(prompts, sp, return_logits=True)
     ls = lm.decode(n_new - 1, sp, return_logits=True)
     torch.cuda.synchronize()
@@ -156,7 +156,7 @@ def test_nano_like_shape(cuda, B):
     prompts = [torch.randint(0, cfg.vocab_size, (n,), generator=g) for n in lens]
     n_new = 10
     forced = torch.randint(0, cfg.vocab_size, (B, n_new), generator=g)
-    got = _tf(lm, [p.tolist() for p in prompts], forced, n_new)
+    got = _tf(lm, [p.tolist() for p in prompts], forced, n_new, eos=cfg.vocab_size - 1)
     for b in range(B):
         _, ref = O.generate(cfg, w, prompts[b], cfg.vocab_size - 1, max_length=512, max_new_tokens=n_new, forced=forced[b], mirror=False)
         _bars(got[b], ref, f"nano-like B={B} slot {b}")
