@@ -37,7 +37,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1, help="utterances per GPU per step (metric is quoted at 1, 8, 64)")
+    ap.add_argument("--batch", type=int, default=0,
+                    help="utterances per GPU per step; default: 1 on one GPU (configs[1]), 64 / N on N GPUs (configs[3])")
     ap.add_argument("--workload", default="fixed", choices=["fixed", "mixed"],
                     help="fixed: every prompt 500 tokens (configs[1]); mixed: prompt lengths U{200..1400}, seeded (configs[2])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -223,6 +224,10 @@ def main_reference(args):
 # B200 arm
 # ----------------------------------------------------------------------------------------------
 _WEIGHTS = {}
+SPEECH_BASE, EOS = 151936, 151670
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE decode_tc_kernel launch (249 steps, batch 1, contexts 500..749)
+# from profiles/decode_tc_b1_r2_ncu_summary.txt (ncu --set full); None until a capture of the current kernel exists
+NCU_TRAFFIC_B1 = 278.65e9
 
 
 def build_engines(device, batch, prefill_tokens=None):
@@ -240,47 +245,117 @@ def build_engines(device, batch, prefill_tokens=None):
     return lm, codec
 
 
-def quick_batch(dev, B, steps=2):
-    """One extra line of the metric at another batch size on this GPU (the metric is quoted at batch 1, 8 and 64):
-    same workload per utterance, inputs resident in HBM, CUDA-event timing, 1 warm-up + `steps` timed passes."""
-    lm, codec = build_engines(dev, B)
-    speech_base, eos = 151936, 151670
-    prompts = synth_prompts(B, lm.shape.vocab_size, speech_base, 4321)
+class _BenchTokenizer:
+    """The two lookups the facade's hot path makes (neutts/neutts.py: _tok_id / speech_base)."""
+
+    def convert_tokens_to_ids(self, name: str) -> int:
+        if name == "<|SPEECH_GENERATION_END|>":
+            return EOS
+        if name.startswith("<|speech_"):
+            return SPEECH_BASE + int(name[9:-2])
+        raise KeyError(name)
+
+
+def make_facade(lm, codec, batch, seed):
+    """The public class (neutts.NeuTTS) around the two engines.  One bench-only shim: a random-weight LM emits
+    arbitrary vocabulary ids, so the id -> code map folds them into the codebook instead of dropping non-speech ids
+    (every utterance then has exactly 250 frames, as a trained model would produce for the workload)."""
+    import warnings
+
+    from neutts import NeuTTS
+
+    class BenchTTS(NeuTTS):
+        def _ids_to_codes(self, ids):
+            return (ids.long() - SPEECH_BASE) % 65536
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return BenchTTS(backbone=lm, codec=codec, tokenizer=_BenchTokenizer(), phonemizer=object(), max_batch=batch, seed=seed)
+
+
+def step_bytes(shape, B, mean_prompt):
+    """Algorithmic HBM bytes of ONE decode step (BASELINE.md §2 / DESIGN.md §4): every bf16 weight once + the KV
+    cache of B sequences at the mean context of the 250-token run + the token's activations."""
+    p_blk = shape.num_layers * ((shape.num_heads + 2 * shape.num_kv_heads) * 64 * (shape.hidden_size + 1) + shape.hidden_size * shape.num_heads * 64
+                                + 3 * shape.hidden_size * shape.intermediate_size + 2 * shape.hidden_size) + shape.hidden_size
+    return 2 * (p_blk + shape.vocab_size * shape.hidden_size) + B * (12288 * (mean_prompt + DECODE / 2 + 1) + 2 * shape.hidden_size)
+
+
+def decode_roofline(lm, B, lens, t_dec, n_steps, launches_per_step):
+    """roofline block for the decode loop, the dominant kernel of the timed region."""
+    peak, how = peaks()
+    sb = step_bytes(lm.shape, B, sum(lens) / len(lens))
+    persistent = launches_per_step is None
+    alg = sb * n_steps if persistent else sb
+    t = t_dec if persistent else t_dec / n_steps
+    return {"bound": "hbm",
+            "kernel": ("decode_tc_kernel (persistent: all layers + lm_head + sampler, %d decode steps per launch)" % n_steps) if persistent
+            else "decode step = CUDA graph of %d kernels (tcgen05 GEMMs, attention, norms, sampler)" % launches_per_step,
+            "achieved": alg / t / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / t / 1e9 / peak,
+            "traffic": NCU_TRAFFIC_B1 if (persistent and B == 1) else None,
+            "traffic_source": "profiles/decode_tc_b1_r2_ncu_summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)",
+            "peak_source": how, "algorithmic_bytes_per_launch": alg, "us_per_launch": t * 1e6,
+            "us_per_decode_step": t_dec / n_steps * 1e6, "algorithmic_bytes_per_step": sb}
+
+
+def time_decode(lm, prompts, seed=5):
+    sp = lm.sampling(EOS, min_new_tokens=DECODE, max_new_tokens=DECODE, seed=seed)
+    lm.prefill(prompts, sp)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    lm.decode(DECODE - 1, sp)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / 1e3
+
+
+def quick_batch(dev, B, steps=2, mixed=False, L=None):
+    """One extra line of the metric at another batch size / workload on this GPU (the metric is quoted at batch 1, 8
+    and 64; configs[2] is the mixed-length batch 64): inputs resident in HBM, CUDA-event timing, 1 warm-up + `steps`
+    timed passes, plus the decode loop alone."""
+    prompts = synth_prompts(B, 217472, SPEECH_BASE, 4321, mixed)
+    lm, codec = build_engines(dev, B, sum(len(p) for p in prompts))
 
     def step(seed):
-        sp = lm.sampling(eos, min_new_tokens=DECODE, max_new_tokens=DECODE, top_k=50, temperature=1.0, seed=seed)
+        sp = lm.sampling(EOS, min_new_tokens=DECODE, max_new_tokens=DECODE, top_k=50, temperature=1.0, seed=seed)
         lm.prefill(prompts, sp)
         lm.decode(DECODE - 1, sp)
-        c = (lm.out_tokens[:B, :DECODE].long() - speech_base).clamp_(0, 65535)[:, None, :]
+        c = ((lm.out_tokens[:B, :DECODE].long() - SPEECH_BASE) % 65536)[:, None, :]
         return codec.decode_code(c)
 
     step(0)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = L.nt_launch_count() if L else 0
     e0.record()
     for i in range(steps):
         step(10 + i)
     e1.record()
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / 1e3 / steps
-    sp = lm.sampling(eos, min_new_tokens=DECODE, max_new_tokens=DECODE, seed=5)
-    lm.prefill(prompts, sp)
-    torch.cuda.synchronize()
-    e0.record()
-    lm.decode(DECODE - 1, sp)
-    e1.record()
-    torch.cuda.synchronize()
-    t_dec = e0.elapsed_time(e1) / 1e3
+    n1 = L.nt_launch_count() if L else 0
+    m0 = L.nt_launch_count() if L else 0
+    t_dec = time_decode(lm, prompts)
+    dec_launches = ((L.nt_launch_count() - m0) if L else 0)
+    lens = [len(p) for p in prompts]
+    # launches of the decode loop alone: subtract the prefill's (measured separately below would cost a pass; the
+    # persistent kernel is exactly one launch, the chain reports its graph size)
+    per_step = None if B <= 8 else max(1, round(dec_launches / DECODE))
+    out = {"per_gpu_batch": B, "workload": ("configs[2]: mixed-length prompts U{200..1400} (mean %.0f)" % (sum(lens) / B)) if mixed else "configs[1] shape, 500-token prompts",
+           "value": AUDIO_S * B / t, "unit": "audio-s/s", "ms_per_step": t * 1e3, "steps": steps,
+           "decode_tok_s": B * (DECODE - 1) / t_dec, "decode_ms_per_token_step": t_dec / (DECODE - 1) * 1e3,
+           "gpu_launches_per_pass": int((n1 - n0) / steps) if L else None,
+           "roofline": decode_roofline(lm, B, lens, t_dec, DECODE - 1, per_step)}
     del lm, codec
     torch.cuda.empty_cache()
-    return {"per_gpu_batch": B, "value": AUDIO_S * B / t, "unit": "audio-s/s", "ms_per_step": t * 1e3, "steps": steps,
-            "decode_tok_s": B * (DECODE - 1) / t_dec, "decode_ms_per_token_step": t_dec / (DECODE - 1) * 1e3}
+    return out
 
 
 def main_b200(args):
     import torch.distributed as td
 
-    from neutts_air_b200 import _lib
+    from neutts_air_b200 import _lib, dist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -292,42 +367,27 @@ def main_b200(args):
     if world > 1:
         td.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
-    B = args.batch
-    speech_base, eos = 151936, 151670
+    # N = 1: configs[1] (batch 1, the configuration the metric is quoted on).  N > 1: configs[3], global batch 64
+    # sharded 64 / N utterances per GPU (strong scaling: the job is fixed, the GPUs split it).
+    B = args.batch if args.batch else (1 if world == 1 else max(1, 64 // world))
+    strong = world > 1 and not args.batch
     mixed = args.workload == "mixed"
-    prompts = synth_prompts(B, 217472, speech_base, 1234 + rank, mixed)
-    lm, codec = build_engines(dev, B, sum(len(p) for p in prompts))
-    pinned_ids = torch.tensor([t for p in prompts for t in p], dtype=torch.int32).pin_memory()
+    prompts = synth_prompts(B, 217472, SPEECH_BASE, 1234 + rank, mixed)
     lens = [len(p) for p in prompts]
-    h2d_bytes = pinned_ids.numel() * 4
-    pcm_host = torch.empty(B, DECODE * HOP, dtype=torch.float32).pin_memory()
-    d2h_bytes = pcm_host.numel() * 4
+    lm, codec = build_engines(dev, B, sum(lens))
+    tts = make_facade(lm, codec, B, seed=777)
+    h2d_bytes = sum(lens) * 4
+    d2h_bytes = B * DECODE * HOP * 4 + B * 256 * 4 + B * 4      # PCM + generated ids + counters read by generate_batch
 
     def codes_from(lm_):
-        c = lm_.out_tokens[:B, :DECODE].long() - speech_base
-        return c.clamp_(0, 65535)[:, None, :]       # random-weight LM may emit text ids; keep the codec input in range
+        return ((lm_.out_tokens[:B, :DECODE].long() - SPEECH_BASE) % 65536)[:, None, :]
 
     def step_device(seed):
         """inputs already resident in HBM; returns PCM on device."""
-        sp = lm.sampling(eos, min_new_tokens=DECODE, max_new_tokens=DECODE, top_k=50, temperature=1.0, seed=seed)
+        sp = lm.sampling(EOS, min_new_tokens=DECODE, max_new_tokens=DECODE, top_k=50, temperature=1.0, seed=seed)
         lm.prefill(prompts, sp)
         lm.decode(DECODE - 1, sp)
         return codec.decode_code(codes_from(lm))
-
-    def step_e2e(seed):
-        """host ids (pinned) -> H2D -> hot path -> D2H PCM (pinned): the call a user makes, minus the text front-end."""
-        sp = lm.sampling(eos, min_new_tokens=DECODE, max_new_tokens=DECODE, top_k=50, temperature=1.0, seed=seed)
-        lm.prefill_packed(pinned_ids, lens, sp)      # H2D copy of the prompt ids from pinned memory happens in here
-        lm.decode(DECODE - 1, sp)
-        pcm = codec.decode_code(codes_from(lm))
-        pcm_host.copy_(pcm[:, 0, :], non_blocking=True)
-        torch.cuda.synchronize()
-        return pcm_host
-
-    def barrier():
-        if world > 1:
-            td.barrier()
-        torch.cuda.synchronize()
 
     def gather(pcm):
         if world > 1:   # the one collective of the path: all-gather of finished waveforms (SURVEY §8e)
@@ -335,6 +395,23 @@ def main_b200(args):
             td.all_gather_into_tensor(out, pcm[:, 0, :].contiguous())
             return out
         return pcm
+
+    def step_e2e(seed):
+        """The call a user makes, minus the text front-end: host prompt ids -> neutts.NeuTTS.infer_from_prompt_ids
+        (pinned H2D of the ids, device-side generation, codec, D2H of the PCM) -> host waveforms, then the waveform
+        all-gather of the sharded job."""
+        tts.seed = seed
+        wavs = tts.infer_from_prompt_ids(prompts, max_new_tokens=DECODE, min_new_tokens=DECODE)
+        if world > 1:
+            mine = list(range(rank * B, rank * B + B))
+            wavs = dist.all_gather_waveforms(wavs, mine, world * B, device=dev, t_max=DECODE * HOP)
+        assert all(len(w) == DECODE * HOP for w in wavs)
+        return wavs
+
+    def barrier():
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
 
     for i in range(args.warmup):
         gather(step_device(i))
@@ -353,28 +430,26 @@ def main_b200(args):
     launches = L.nt_launch_count() - n0
     clk = clocks.stop() if rank == 0 else None
 
-    # decode-only tokens/s (LM only, generated tokens / decode-loop time)
-    sp = lm.sampling(eos, min_new_tokens=DECODE, max_new_tokens=DECODE, seed=5)
-    lm.prefill(prompts, sp)
-    torch.cuda.synchronize()
+    # the parts, each timed alone with CUDA events
+    m0 = L.nt_launch_count()
+    t_dec = time_decode(lm, prompts)
+    dec_launches = L.nt_launch_count() - m0
+    sp = lm.sampling(EOS, min_new_tokens=DECODE, max_new_tokens=DECODE, seed=5)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    lm.decode(DECODE - 1, sp)
-    e1.record()
-    torch.cuda.synchronize()
-    t_dec = e0.elapsed_time(e1) / 1e3
+    m1 = L.nt_launch_count()
     e0.record()
     lm.prefill(prompts, sp)
     e1.record()
     torch.cuda.synchronize()
     t_pre = e0.elapsed_time(e1) / 1e3
+    pre_launches = L.nt_launch_count() - m1
     e0.record()
     codec.decode_code(codes_from(lm))
     e1.record()
     torch.cuda.synchronize()
     t_codec = e0.elapsed_time(e1) / 1e3
 
-    # end-to-end through host buffers
+    # end-to-end through the public API and host buffers
     for i in range(2):
         step_e2e(i)
     barrier()
@@ -383,26 +458,6 @@ def main_b200(args):
         step_e2e(200 + i)
     barrier()
     t_e2e = time.perf_counter() - t0
-
-    # roofline of the dominant kernel: lm_head GEMV (V x H bf16 = 390 MB > 126 MB L2, so every launch streams from HBM)
-    roof = None
-    if B <= 4:
-        h = torch.randn(B, lm.shape.hidden_size, device=dev)
-        for _ in range(3):
-            lm.head_gemv(h)
-        reps = 20
-        e0.record()
-        for _ in range(reps):
-            lm.head_gemv(h)
-        e1.record()
-        torch.cuda.synchronize()
-        t_k = e0.elapsed_time(e1) / 1e3 / reps
-        alg = lm.shape.vocab_size * lm.shape.hidden_size * 2 + B * (lm.shape.hidden_size * 4 + lm.shape.vocab_size * 4)
-        peak, how = peaks()
-        roof = {"bound": "hbm", "kernel": "gemv_kernel<lm_head>", "achieved": alg / t_k / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg / t_k / 1e9 / peak, "traffic": 389.8e6 if B == 1 else None,
-                "traffic_source": "dram__bytes_read+write of one ncu --set full capture, profiles/head_gemv_r1_summary.txt",
-                "peak_source": how, "us_per_launch": t_k * 1e6, "algorithmic_bytes": alg}
 
     times = torch.tensor([t_dev, t_e2e, t_dec, t_pre, t_codec], device=dev, dtype=torch.float64)
     if world > 1:
@@ -413,38 +468,36 @@ def main_b200(args):
             td.destroy_process_group()
         return
     total_audio = AUDIO_S * B * world * args.steps
-    # algorithmic bytes of one decode step, averaged over contexts 500..749
-    cfgs = lm.shape
-    p_blk = cfgs.num_layers * ((cfgs.num_heads + 2 * cfgs.num_kv_heads) * 64 * (cfgs.hidden_size + 1) + cfgs.hidden_size * cfgs.num_heads * 64
-                               + 3 * cfgs.hidden_size * cfgs.intermediate_size + 2 * cfgs.hidden_size) + cfgs.hidden_size
-    step_bytes = 2 * (p_blk + cfgs.vocab_size * cfgs.hidden_size) + B * (12288 * (sum(lens) / len(lens) + DECODE / 2 + 1) + 2 * cfgs.hidden_size)
-    peak, how = peaks()
+    n_dec_launch = dec_launches - pre_launches            # time_decode = one prefill + the decode loop
+    per_step = None if n_dec_launch <= 2 else max(1, round(n_dec_launch / (DECODE - 1)))
+    roof = decode_roofline(lm, B, lens, t_dec, DECODE - 1, per_step)
+    roof["share_of_timed_region"] = t_dec / (t_dev / args.steps)
     line = {
         "metric": "audio-sec/sec (RTF), NeuTTS-Air 500 prefill / 250 decode + NeuCodec decode",
         "value": total_audio / t_dev, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "bf16 weights+KV / f32 accumulate (LM), tf32 tensor cores (codec)", "data": "synthetic",
         "config": {"workload": (f"configs[2]: mixed-length prompts U{{200..1400}} (mean {sum(lens) / len(lens):.0f}) / 250 decode tokens + NeuCodec "
                                 f"decode to 24 kHz, batch={B} per GPU" if mixed else
-                                f"configs[1]: 500 prefill / 250 decode tokens + NeuCodec decode to 24 kHz, batch={B} per GPU"),
+                                (f"configs[3]: global batch {B * world} sharded {B} utterances/GPU over {world} GPUs, 500 prefill / 250 decode tokens + "
+                                 "NeuCodec decode to 24 kHz, NCCL waveform all-gather" if strong else
+                                 f"configs[1]: 500 prefill / 250 decode tokens + NeuCodec decode to 24 kHz, batch={B} per GPU")),
                    "per_gpu_batch": B, "global_batch": B * world, "sharding": "utterances one-per-GPU-slot, weights replicated, "
                    "one all-gather of waveforms" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2: 1.1 GB of weights stream per decode step (L2 = 126 MB)", "weights": "seeded random, inferred Air/NeuCodec shapes"},
         "decode_tok_s": B * world * (DECODE - 1) / t_dec,
-        "decode_step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes * (DECODE - 1) / t_dec / 1e9,
-                                 "frac": step_bytes * (DECODE - 1) / t_dec / 1e9 / peak, "peak_source": how},
+        "roofline": roof,
         "breakdown_ms": {"prefill": t_pre * 1e3, "decode_249_steps": t_dec * 1e3, "codec": t_codec * 1e3},
         "e2e": {"value": total_audio / t_e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": t_e2e / args.steps * 1e3},
+                "ms_per_step": t_e2e / args.steps * 1e3, "api": "neutts.NeuTTS.infer_from_prompt_ids" + (" + dist.all_gather_waveforms" if world > 1 else "")},
         "gpu_launches": int(launches),
         "clocks": clk,
     }
-    if roof:
-        line["roofline"] = roof
     if world == 1 and not args.no_sweep:
-        del lm, codec
+        del lm, codec, tts
         torch.cuda.empty_cache()
-        line["batches"] = [quick_batch(dev, b) for b in (8, 64) if b != B]
+        line["batches"] = [quick_batch(dev, b, L=L) for b in (8, 64) if b != B]
+        line["extra_configs"] = [quick_batch(dev, 64, mixed=True, L=L)]
     if not args.no_cpu_baseline and world == 1:
         try:
             v, ms, sample, cores, parts = reference_measure(1, 0)

@@ -286,7 +286,32 @@ class NeuTTS:
         prompt = self._apply_chat_template(ref_codes, ref_text, text)
         return self._stream(prompt, [int(c) for c in (ref_codes.tolist() if hasattr(ref_codes, "tolist") else ref_codes)])
 
+    def infer_stream_batch(self, texts: Sequence[str], ref_codes: Sequence, ref_texts: Sequence[str]) -> Generator[list, None, None]:
+        """Streaming synthesis of up to ``max_batch`` utterances at once (BASELINE.json configs[4]; the reference
+        streams one utterance, ``neutts/neutts.py:373-465``).  Every yield is a list with one entry per utterance:
+        the next audio chunk (float32, cross-faded exactly as in ``infer_stream``) or ``None`` when that utterance
+        has nothing new.  The sequences decode in lock-step in ONE persistent-kernel launch per round; the windows
+        that are due are gathered on the device from the code history and go through the codec as one batch."""
+        if not (len(texts) == len(ref_codes) == len(ref_texts)):
+            raise ValueError("texts, ref_codes and ref_texts must have the same length")
+        prompts = [self._apply_chat_template(c, rt, t) for t, c, rt in zip(texts, ref_codes, ref_texts)]
+        refs = [[int(c) for c in (rc.tolist() if hasattr(rc, "tolist") else rc)] for rc in ref_codes]
+        return self._stream_batch(prompts, refs)
+
     def _stream(self, prompt, ref_codes) -> Generator[np.ndarray, None, None]:
+        for out in self._stream_batch([prompt], [list(ref_codes)]):
+            if out[0] is not None:
+                yield out[0]
+
+    def _stream_batch(self, prompts, refs) -> Generator[list, None, None]:
+        """Window geometry of the reference (``neutts/neutts.py:87-91,401-421,443-465``): once F + LA undecoded frames
+        exist, the codec decodes [n_dec - LB - OV, n_dec + F + LA) and the slice [n_dec - OV, n_dec + F + OV) is
+        cross-faded at stride F * hop; a ragged tail closes the stream.  ``streaming_frames_per_chunk`` may be set to
+        50 for the "codec every 50 tokens" configuration BASELINE.json names.
+
+        State per slot: the code history (reference codes, then generated ones) lives ON THE DEVICE next to the
+        engine's ``out_tokens``; a round is  decode(k steps, all slots) -> absorb the new tokens into the history
+        with device ops -> one small D2H read of (n_generated, done, history length) -> batched codec call."""
         hop, F, LA, LB, OV = self.hop_length, self.streaming_frames_per_chunk, self.streaming_lookforward, \
             self.streaming_lookback, self.streaming_overlap_frames
         eos = self._tok_id("<|SPEECH_GENERATION_END|>")
@@ -294,41 +319,115 @@ class NeuTTS:
         lm = self.backbone
         if not hasattr(lm, "prefill"):
             raise NotImplementedError("Streaming needs the neutts_air_b200.SpeechLM backbone")
-        limit = min(self.max_context - len(prompt), lm.max_new)
-        if limit < 1:
+        B = len(prompts)
+        limits = [min(self.max_context - len(p), lm.max_new) for p in prompts]
+        if min(limits) < 1:
             raise ValueError("prompt already at max_length")
-        sp = lm.sampling(eos, 50, limit, 50, 1.0, seed)
-        cache = list(ref_codes)              # code history: reference codes, then generated ones
-        n_dec = len(cache)
-        fade = _CrossFade(self.streaming_stride_samples)
-        lm.prefill([prompt], sp)             # samples the first token
-        produced = 0
+        limit = max(limits)
+        sp = lm.sampling(eos, 50, limit, 50, 1.0, seed) if min(limits) == limit else lm.sampling(eos, 50, limit, 50, 1.0, seed, limits=limits)
+        dev = lm.out_tokens.device
+        base = self.speech_base
+        shape = getattr(self.codec, "shape", None)
+        n_codes = getattr(shape, "fsq_levels", 4) ** getattr(shape, "fsq_dims", 8)
+        cap = max(len(r) for r in refs) + limit
+        hist = torch.zeros(B, cap + 1, dtype=torch.long, device=dev)          # column `cap` is a scratch slot for masked writes
+        for b, r in enumerate(refs):
+            hist[b, : len(r)] = torch.as_tensor(r, dtype=torch.long)
+        hlen = torch.tensor([len(r) for r in refs], dtype=torch.long, device=dev)
+        absorbed = torch.zeros(B, dtype=torch.long, device=dev)                # generated tokens already looked at
+        n_dec = [len(r) for r in refs]
+        fades = [_CrossFade(self.streaming_stride_samples) for _ in range(B)]
+        tail_done = [False] * B
+        lim_t = torch.tensor(limits, dtype=torch.long)
+
+        def absorb(lo: int, hi: int):
+            """tokens [lo, hi) of every slot -> history (non-speech ids dropped, as the reference's regex does)"""
+            if hi <= lo:
+                return
+            ngen = lm.n_generated[:B].long()
+            seg = lm.out_tokens[:B, lo:hi].long() - base
+            cols = torch.arange(lo, hi, device=dev)[None, :]
+            valid = (cols >= absorbed[:, None]) & (cols < ngen[:, None]) & (seg >= 0) & (seg < n_codes)
+            pos = hlen[:, None] + torch.cumsum(valid, 1) - 1
+            hist.scatter_(1, torch.where(valid, pos, torch.full_like(pos, cap)), seg)
+            hlen.add_(valid.sum(1))
+            absorbed.copy_(torch.minimum(ngen, torch.full_like(ngen, hi)))
+
+        def decode_windows(jobs):
+            """jobs: (slot, t0, t1, s0, s1 | None).  Same-length windows share one codec call."""
+            out = {}
+            by_len = {}
+            for j in jobs:
+                by_len.setdefault(j[2] - j[1], []).append(j)
+            cbatch = max(1, getattr(self.codec, "max_batch", 1))
+            for n, grp in by_len.items():
+                for g0 in range(0, len(grp), cbatch):
+                    g = grp[g0: g0 + cbatch]
+                    rows = torch.tensor([j[0] for j in g], device=dev)
+                    idx = torch.tensor([j[1] for j in g], device=dev)[:, None] + torch.arange(n, device=dev)[None, :]
+                    codes = hist[rows[:, None], idx][:, None, :]
+                    with torch.no_grad():
+                        pcm = self.codec.decode_code(codes.to(self.codec.device))
+                    pcm = pcm[:, 0, :].cpu().numpy()
+                    for r, (b, t0, t1, s0, s1) in enumerate(g):
+                        wav = self._watermark(pcm[r])
+                        out.setdefault(b, []).append(wav[max(s0, 0):] if s1 is None else wav[s0:s1])
+            return out
+
+        lm.prefill(prompts, sp)             # samples the first token of every slot
+        lo, hi = 0, 1
         while True:
-            ngen = int(lm.n_generated[0])
-            finished = bool(int(lm.done[0])) or ngen >= limit
-            cache += self._ids_to_codes(lm.out_tokens[0, produced:ngen].cpu()).tolist()
-            produced = ngen
-            while len(cache) - n_dec >= F + LA:
-                t0 = max(n_dec - LB - OV, 0)
-                # the reference slices up to n_dec + F + LA + OV, but tokens arrive one at a time there, so
-                # its cache never holds more than n_dec + F + LA entries when a chunk fires (:401-415)
-                t1 = n_dec + F + LA
-                s0 = (n_dec - t0) * hop
-                wav = self._watermark(self._decode(cache[t0:t1]))[s0: s0 + (F + 2 * OV) * hop]
-                n_dec += F
-                yield fade.push(wav)
-            if finished:
+            absorb(lo, hi)
+            st = torch.stack((lm.n_generated[:B].long(), lm.done[:B].long(), hlen)).cpu()   # the round's one D2H read
+            ngen_h, done_h, hlen_h = st[0], st[1], st[2]
+            finished = [bool(done_h[b]) or int(ngen_h[b]) >= limits[b] for b in range(B)]
+            jobs = []
+            for b in range(B):
+                while int(hlen_h[b]) - n_dec[b] >= F + LA:
+                    t0 = max(n_dec[b] - LB - OV, 0)
+                    # the reference slices up to n_dec + F + LA + OV, but tokens arrive one at a time there, so
+                    # its cache never holds more than n_dec + F + LA entries when a chunk fires (:401-415)
+                    t1 = n_dec[b] + F + LA
+                    s0 = (n_dec[b] - t0) * hop
+                    jobs.append((b, t0, t1, s0, s0 + (F + 2 * OV) * hop))
+                    n_dec[b] += F
+            out = [None] * B
+            if jobs:
+                for b, wavs in decode_windows(jobs).items():
+                    out[b] = np.concatenate([fades[b].push(w) for w in wavs])
+            # ragged tail of a slot that finished (neutts/neutts.py:443-465), once its regular chunks are out
+            tails = []
+            all_finished = all(finished)
+            for b in range(B):
+                if finished[b] and not tail_done[b] and (all_finished or out[b] is None):
+                    tail_done[b] = True
+                    n = int(hlen_h[b])
+                    if n > n_dec[b]:
+                        rem = n - n_dec[b]
+                        t0 = max(n - (LB + OV + rem), 0)
+                        tails.append((b, t0, n, (n - t0 - rem - OV) * hop, None))
+                    elif fades[b].acc.shape[0]:
+                        flush = fades[b].push(np.zeros(0, np.float32), final=True)
+                        out[b] = flush if out[b] is None else np.concatenate((out[b], flush))
+            if all_finished and any(o is not None for o in out) and tails:
+                yield out                    # regular chunks first: a tail is its own yield, as in the reference
+                out = [None] * B
+            if tails:
+                for b, wavs in decode_windows(tails).items():
+                    t = fades[b].push(wavs[0], final=True)
+                    out[b] = t if out[b] is None else np.concatenate((out[b], t))
+            if any(o is not None for o in out):
+                yield out
+            if all_finished:
                 break
-            # decode just enough steps for the next chunk to fire (non-speech ids may make it take another pass)
-            lm.decode(min(F + LA - (len(cache) - n_dec), limit - ngen), sp)
-        if len(cache) > n_dec:               # ragged tail (neutts/neutts.py:443-465)
-            rem = len(cache) - n_dec
-            t0 = max(len(cache) - (LB + OV + rem), 0)
-            s0 = (len(cache) - t0 - rem - OV) * hop
-            wav = self._watermark(self._decode(cache[t0:]))[max(s0, 0):]
-            yield fade.push(wav, final=True)
-        elif fade.acc.shape[0]:
-            yield fade.push(np.zeros(0, np.float32), final=True)
+            # decode just enough steps for the next chunk of the most advanced unfinished slot to fire (non-speech
+            # ids may make it take another pass); finished slots idle inside the kernel
+            need = min(F + LA - (int(hlen_h[b]) - n_dec[b]) for b in range(B) if not finished[b])
+            room = min(limits[b] - int(ngen_h[b]) for b in range(B) if not finished[b])
+            steps = max(1, min(need, room))
+            lo = int(ngen_h.min())
+            lm.decode(steps, sp)
+            hi = int(ngen_h.max()) + steps
 
     def encode_reference(self, ref_audio_path):
         """wav -> NeuCodec codes (``neutts/neutts.py:266-271``).  The encoder is outside the hot path; this

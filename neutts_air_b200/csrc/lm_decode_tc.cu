@@ -178,7 +178,7 @@ __host__ __device__ constexpr size_t tc_attn_layout_bytes(int aw) {
 }
 
 // ------------------------------------------------------------------------------------------ the kernel
-template <int NT, bool HILO>
+template <int NT, bool HILO, bool FOLD>
 __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_constant__ TcParams P) {
   constexpr int CHUNK = NT * 128;            // bytes of one B-operand k-block
   constexpr int NTOK = HILO ? 8 : NT;        // token slots on the N axis
@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
     auto pm = [&](int id) { if (tid == 0 && prof.fine) prof.mark(id); };
     const int n_rep = P.n_heads / P.n_kv;
     const int split_cap = P.split_cap;
-    const bool fold_cta = P.fold_in_cta != 0;
+    constexpr bool fold_cta = FOLD;   // batch <= 4: consumers fold the split-K slices themselves (no fold phases, no barriers)
     const int I = P.inter;
     float* xf = reinterpret_cast<float*>(uni + 14 * CHUNK);   // fold_in_cta: fp32 folded rows [B][H] behind the B chunks
     float* xw = xf + 4096;                                      // ... and the RMSNorm weight row [H] (H <= 1024)
@@ -1008,22 +1008,140 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       const float inv_t = 1.0f / P.samp.sp.temperature;
       const bool mask_eos = ms->mask_eos[b] != 0;
       const int eos = P.samp.sp.eos_id;
+      const bool stateless = false;
+      const int ngen = __ldcg(P.samp.n_generated + b);
+      const bool is_done = __ldcg(P.samp.done + b) != 0;
+      float2* h2dst = fold_cta ? P.h2 + (static_cast<long long>(fold_no & 1) * B + b) * H : nullptr;
+      const float h2stamp = __int_as_float(P.hstamp_base + fold_no);
+      const float* lg = P.logits + static_cast<long long>(b) * V;
       pm(120);
+      // ---- direct path (large vocabularies).  Every thread takes the largest of its <= 8 tile maxima; the top_k-th
+      //      largest of those 256 values, L, is a valid candidate threshold: at least top_k distinct tiles reach it,
+      //      so the top_k logits all do (it sits a hair below the exact top_k-th tile maximum, since two of the best
+      //      tiles rarely share a thread).  Tiles whose maximum reaches L are scanned, logits >= L are ranked in
+      //      shared memory by (score desc, index asc).  Two round trips to L2, six CTA barriers, no radix passes.
+      {
+        constexpr int kPer = 8, kTileCap = 256, kCandCap = 512;
+        const int ktop = min(P.samp.sp.top_k, kTopKeep);
+        float* gmax = reinterpret_cast<float*>(keys);                         // [256]
+        int* tl = reinterpret_cast<int*>(keys + kConsumerThreads);            // [kTileCap]
+        Cand* fc = reinterpret_cast<Cand*>(keys + kConsumerThreads + kTileCap);  // [kCandCap]
+        int* cnt = ms->sel;                                                   // [0] tiles, [1] candidates, [2] L
+        if (nt <= kPer * kConsumerThreads && key_cap >= kConsumerThreads + kTileCap + 2 * kCandCap) {
+          float tm[kPer];
+          float best = -INFINITY;
+#pragma unroll
+          for (int u = 0; u < kPer; ++u) {
+            const int i = tid + u * kConsumerThreads;
+            tm[u] = (i < nt) ? __ldcg(P.tmax + static_cast<long long>(b) * nt + i) : -INFINITY;
+          }
+#pragma unroll
+          for (int u = 0; u < kPer; ++u) best = fmaxf(best, tm[u]);
+          gmax[tid] = best;
+          if (tid < 3) cnt[tid] = (tid == 2) ? __float_as_int(-INFINITY) : 0;
+          csync();
+          int rank = 0;   // (value desc, thread asc) is a total order: the ranks are a permutation of 0..255
+          for (int j4 = 0; j4 < kConsumerThreads; j4 += 4) {
+            const float4 g = *reinterpret_cast<const float4*>(gmax + j4);
+            rank += (g.x > best || (g.x == best && j4 < tid)) ? 1 : 0;
+            rank += (g.y > best || (g.y == best && j4 + 1 < tid)) ? 1 : 0;
+            rank += (g.z > best || (g.z == best && j4 + 2 < tid)) ? 1 : 0;
+            rank += (g.w > best || (g.w == best && j4 + 3 < tid)) ? 1 : 0;
+          }
+          if (rank == ktop - 1) cnt[2] = __float_as_int(best);
+          csync();
+          const float L = __int_as_float(cnt[2]);
+          pm(121);
+          if (L > -INFINITY) {   // CTA-uniform
+#pragma unroll
+            for (int u = 0; u < kPer; ++u) {
+              const bool hit = tm[u] >= L;   // padding slots hold -inf
+              const uint32_t m = __ballot_sync(0xffffffffu, hit);
+              if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&cnt[0], __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const int o = base + __popc(m & ((1u << lane) - 1u));
+                if (hit && o < kTileCap) tl[o] = tid + u * kConsumerThreads;
+              }
+            }
+            csync();
+            const int ntl = cnt[0];
+            pm(122);
+            if (ntl <= kTileCap) {   // CTA-uniform
+              for (int j0 = warp; j0 < ntl; j0 += 4 * kConsumerWarps) {   // 4 tiles per warp in flight
+                float4 x[4];
+                int tile[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int j = j0 + u * kConsumerWarps;
+                  tile[u] = (j < ntl) ? tl[j] : -1;
+                  x[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                  if (tile[u] >= 0) {
+                    const int r0 = tile[u] * 128 + lane * 4;
+                    if (r0 + 3 < V) {
+                      x[u] = __ldcg(reinterpret_cast<const float4*>(lg + r0));
+                    } else {
+                      if (r0 < V) x[u].x = __ldcg(lg + r0);
+                      if (r0 + 1 < V) x[u].y = __ldcg(lg + r0 + 1);
+                      if (r0 + 2 < V) x[u].z = __ldcg(lg + r0 + 2);
+                    }
+                  }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  if (tile[u] < 0) continue;   // warp-uniform
+                  const int r0 = tile[u] * 128 + lane * 4;
+                  const float xv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const float val = (mask_eos && r0 + q == eos) ? -INFINITY : xv[q] * inv_t;   // rows >= V stayed -inf
+                    const bool hit = val >= L;
+                    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                    if (m) {
+                      int base = 0;
+                      if (lane == 0) base = atomicAdd(&cnt[1], __popc(m));
+                      base = __shfl_sync(0xffffffffu, base, 0);
+                      const int o = base + __popc(m & ((1u << lane) - 1u));
+                      if (hit && o < kCandCap) fc[o].v = val, fc[o].i = r0 + q;
+                    }
+                  }
+                }
+              }
+              csync();
+              const int nc = cnt[1];
+              pm(123);
+              if (nc <= kCandCap) {   // CTA-uniform
+                const int k2 = min(ktop, nc);
+                for (int i = tid; i < nc; i += kConsumerThreads) {
+                  const Cand me = fc[i];
+                  int r = 0;
+                  for (int j = 0; j < nc; ++j) r += cand_before(fc[j], me) ? 1 : 0;
+                  if (r < k2) win[r] = me;
+                }
+                csync();
+                pm(124);
+                sample_finish(P.samp, b, k2, win, s_tok, stateless, ngen, is_done, csync, h2dst, h2stamp);
+                pm(125);
+                return;
+              }
+            }
+          }
+          csync();   // leave the direct path together (its scratch aliases the general path's keys)
+        }
+      }
       for (int i = tid; i < nt; i += kConsumerThreads) keys[i] = f2key(__ldcg(P.tmax + static_cast<long long>(b) * nt + i));
       if (tid < 64) tiles[tid] = -1, counts[tid] = 0;
       csync();
       const int k = min(min(P.samp.sp.top_k, kTopKeep), nt);
       uint32_t thr;
       int take_eq;
-      pm(121);
       radix_select_kth(keys, nt, k, scratch, thr, take_eq, csync);
-      pm(122);
       // fewer tiles than top_k: the tile maxima bound nothing, every logit of every tile is a candidate
       const uint32_t cthr = nt < P.samp.sp.top_k ? 1u : thr;
       // the k tiles: maxima above the threshold, then the first take_eq tiles (index order) that equal it
       compact_topk(keys, nt, thr, take_eq, scratch, csync, [&](int slot, int i) { tiles[slot] = i; });
       csync();
-      const float* lg = P.logits + static_cast<long long>(b) * V;
       auto tile_keys = [&](int tile, uint32_t (&kk)[4]) {   // this lane's 4 logits of the tile -> processed keys
         const int r0 = tile * 128 + lane * 4;
         float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
@@ -1041,11 +1159,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       };
       // ---- fast path: the candidates (key >= threshold) of the chosen tiles go straight into shared memory; all loads
       //      of a warp's tiles are in flight together (one round trip to L2), the exact top-k is a rank sort.
-      const bool stateless = false;
-      const int ngen = __ldcg(P.samp.n_generated + b);
-      const bool is_done = __ldcg(P.samp.done + b) != 0;
-      float2* h2dst = fold_cta ? P.h2 + (static_cast<long long>(fold_no & 1) * B + b) * H : nullptr;
-      const float h2stamp = __int_as_float(P.hstamp_base + fold_no);
       constexpr int kFastCap = 512;
       Cand* fc = reinterpret_cast<Cand*>(keys + ((nt + 3) & ~3));
       int* fcnt = &ms->sel[1];
@@ -1081,7 +1194,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         }
       }
       csync();
-      pm(123);
       const int nc = fast_fits ? *fcnt : kFastCap + 1;
       if (nc <= kFastCap) {
         const int k2 = min(min(P.samp.sp.top_k, kTopKeep), nc);
@@ -1092,9 +1204,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
           if (rank < k2) win[rank] = me;
         }
         csync();
-        pm(124);
         sample_finish(P.samp, b, k2, win, s_tok, stateless, ngen, is_done, csync, h2dst, h2stamp);
-        pm(125);
         return;
       }
       // ---- general path (thousands of candidates: tiny vocabularies, or exact ties at the threshold)
@@ -1181,60 +1291,94 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       cache_pages();
       fence_proxy_async_all();   // KV rows appended in earlier steps (generic proxy, behind grid barriers) -> this step's TMA reads
       csync();
-      if (fold_cta) {
+      // Both layer loops are written as ONE loop over half-layers / segments with a single call site per building block:
+      // the blocks are big inlined lambdas, and a kernel whose layer body does not fit the instruction cache pays for it
+      // in every phase (the first version of this loop compiled to 510 KB of SASS).
+      if constexpr (FOLD) {
         // ---------------- batch <= 4: no grid barrier inside the layers, every hand-off is polled
-        for (int l = 0; l < L; ++l) {
+        for (int hl = 0; hl <= 2 * L; ++hl) {
+          const int l = hl >> 1;
+          const bool second = (hl & 1) != 0, head = hl == 2 * L;
           const int st = stamp_of(step, l);
           prof.fine = prof.buf != nullptr && l == 2;
-          attn_prefetch(l);
-          if (plan.n[kPhQ] > 0) fold_stage(P.pd2, l > 0 ? P.sd : 0, stamp_of(step, l - 1), H, P.ln1[l], kPhQ, plan.fold_q != 0);
+          // fold (residual + split-K slices of the previous GEMM) + RMSNorm + B-operand staging
+          const float2* parts = second ? P.po2 : P.pd2;
+          const int nparts = second ? P.so : (l > 0 ? P.sd : 0);
+          const int pstamp = second ? st : stamp_of(step, l - 1);
+          const float* norm_w = head ? P.final_norm : (second ? P.ln2[l] : P.ln1[l]);
+          const int sph = head ? -1 : (second ? (plan.gu_split ? kPhG : -1) : kPhQ);
+          const bool writer = !head && (second ? plan.fold_g != 0 : plan.fold_q != 0);
+          const bool need = head ? n_head_tiles > 0 : plan.n[second ? kPhG : kPhQ] > 0;
+          if (!second && !head) attn_prefetch(l);
+          if (need) fold_stage(parts, nparts, pstamp, H, norm_w, sph, writer);
           else ++fold_no;
-          epi_partials(kPhQ, P.pq2, P.qkv_n, st);
-          if (tid == 0) prof.mark(100);
-          attention_phase(l, st);
-          if (tid == 0) prof.mark(101);
-          if (plan.n[kPhO] > 0) stage_attn(st);
-          epi_partials(kPhO, P.po2, H, st);
-          if (tid == 0) prof.mark(102);
-          if (plan.n[kPhG] > 0) fold_stage(P.po2, P.so, st, H, P.ln2[l], plan.gu_split ? kPhG : -1, plan.fold_g != 0);
-          else ++fold_no;
-          if (plan.gu_split) epi_partials(kPhG, P.pg2, 2 * I, st);
-          else epi_swiglu(st);
-          if (tid == 0) prof.mark(103);
-          if (plan.n[kPhD] > 0) stage_act(st);
-          epi_partials(kPhD, P.pd2, H, st);
-          if (tid == 0) prof.mark(104);
+          if (head) break;
+          if (second && !plan.gu_split) {
+            epi_swiglu(st);
+            if (tid == 0) prof.mark(103);
+            if (plan.n[kPhD] > 0) stage_act(st);
+            epi_partials(kPhD, P.pd2, H, st);
+            if (tid == 0) prof.mark(104);
+            continue;
+          }
+          for (int e = 0; e < 2; ++e) {   // the two GEMMs of the half-layer: qkv | o_proj, or gate/up | down
+            if (e == 1) {
+              if (!second) {
+                attention_phase(l, st);
+                if (tid == 0) prof.mark(101);
+                if (plan.n[kPhO] > 0) stage_attn(st);
+              } else if (plan.n[kPhD] > 0) {
+                stage_act(st);
+              }
+            }
+            const int ph = (second ? kPhG : kPhQ) + e;   // kPhQ, kPhO | kPhG, kPhD
+            float2* part = ph == kPhQ ? P.pq2 : (ph == kPhO ? P.po2 : (ph == kPhG ? P.pg2 : P.pd2));
+            const int rows = ph == kPhQ ? P.qkv_n : (ph == kPhG ? 2 * I : H);
+            epi_partials(ph, part, rows, st);
+            if (tid == 0) prof.mark(100 + ph + (ph > 0 ? 1 : 0));   // 100 qkv, 102 o_proj, 103 gate/up, 104 down
+          }
         }
-        if (n_head_tiles > 0) fold_stage(P.pd2, L > 0 ? P.sd : 0, stamp_of(step, L - 1), H, P.final_norm, -1, false);
-        else ++fold_no;
       } else {
-        // ---------------- batch > 4: token-owner fold phases feed the consumers by TMA (3 barriers per layer)
+        // ---------------- batch > 4: token-owner fold phases feed the consumers by TMA (3 barriers per layer).
+        // Segments of a layer, each entered through a grid barrier whose post step fetches the B operand:
+        //   0: qkv epilogue, attention, merge + o_proj, fold -> 1: gate/up + SwiGLU -> 2: down_proj, fold
         fold_phase(nullptr, 0, 0, H, L > 0 ? P.ln1[0] : P.final_norm);
-        if (L > 0) grid_sync([&] { load_bop_split(xmap, kPhQ); });
-        else grid_sync([&] { load_bop_full(xmap, n_head_tiles > 0); });
-        for (int l = 0; l < L; ++l) {
+        for (int q = 0;; ++q) {
+          const int l = q / 3, seg = q - 3 * l;
           const int st = stamp_of(step, l);
+          const bool head = l == L;
+          {
+            const bool full = head || seg == 1;
+            const CUtensorMap* m = seg == 2 ? amap : xmap;
+            const int lph = seg == 0 ? kPhQ : kPhD;
+            const bool need = head ? n_head_tiles > 0 : plan.n[kPhG] > 0;
+            grid_sync([&] {
+              if (full) load_bop_full(m, need);
+              else load_bop_split(m, lph);
+            });
+          }
+          if (head) break;
           prof.fine = prof.buf != nullptr && l == 2;
-          epi_partials(kPhQ, P.pq2, P.qkv_n, st);
-          if (tid == 0) prof.mark(100);
-          attention_phase(l, st);
-          if (tid == 0) prof.mark(101);
-          if (plan.n[kPhO] > 0) stage_attn(st);
-          epi_partials(kPhO, P.po2, H, st);
-          if (tid == 0) prof.mark(102);
-          fold_phase(P.po2, P.so, st, H, P.ln2[l]);
-          if (tid == 0) prof.mark(105);
-          grid_sync([&] { load_bop_full(xmap, plan.n[kPhG] > 0); });
-          epi_swiglu(st);
-          if (tid == 0) prof.mark(103);
-          grid_sync([&] { load_bop_split(amap, kPhD); });
-          epi_partials(kPhD, P.pd2, H, st);
-          if (tid == 0) prof.mark(104);
+          if (seg == 1) {
+            epi_swiglu(st);
+            if (tid == 0) prof.mark(103);
+            continue;
+          }
+          for (int e = (seg == 0 ? 0 : 1); e < 2; ++e) {   // segment 0: qkv then o_proj; segment 2: down_proj
+            const int ph = seg == 0 ? (e == 0 ? kPhQ : kPhO) : kPhD;
+            if (ph == kPhO) {
+              attention_phase(l, st);
+              if (tid == 0) prof.mark(101);
+              if (plan.n[kPhO] > 0) stage_attn(st);
+            }
+            float2* part = ph == kPhQ ? P.pq2 : (ph == kPhO ? P.po2 : P.pd2);
+            epi_partials(ph, part, ph == kPhQ ? P.qkv_n : H, st);
+            if (tid == 0) prof.mark(100 + ph + (ph > 0 ? 1 : 0));   // 100 qkv, 102 o_proj, 103 gate/up, 104 down
+          }
           const bool last = l + 1 == L;
-          fold_phase(P.pd2, P.sd, st, H, last ? P.final_norm : P.ln1[l + 1]);
-          if (tid == 0) prof.mark(106);
-          if (last) grid_sync([&] { load_bop_full(xmap, n_head_tiles > 0); });
-          else grid_sync([&] { load_bop_split(xmap, kPhQ); });
+          if (seg == 0) fold_phase(P.po2, P.so, st, H, P.ln2[l]);
+          else fold_phase(P.pd2, P.sd, st, H, last ? P.final_norm : P.ln1[l + 1]);
+          if (tid == 0) prof.mark(seg == 0 ? 105 : 106);
         }
       }
       // ---- lm_head
@@ -1336,6 +1480,7 @@ int tc_build_plan(const TcShape& s, int G, bool flat, TcPlan* plan, unsigned cha
   auto split_phase = [&](int ph, int T, int KB, int* slices) -> bool {
     int S = nr / T;
     const int want = ph == kPhQ ? ov[0] : (ph == kPhO ? ov[1] : ov[2]);
+    if (flat && ph != kPhD && S > (KB + 1) / 2) S = (KB + 1) / 2;   // measured at batch 1: 7 slices 702 us / step, 14 slices 759
     if (want > 0) S = want;
     if (S < 1) S = 1;
     if (S > KB) S = KB;
@@ -1377,9 +1522,9 @@ int tc_build_plan(const TcShape& s, int G, bool flat, TcPlan* plan, unsigned cha
   return NT_OK;
 }
 
-template <int NT, bool HILO>
+template <int NT, bool HILO, bool FOLD>
 static int launch_tc(TcParams& P, int num_sms, cudaStream_t stream) {
-  auto kern = decode_tc_kernel<NT, HILO>;
+  auto kern = decode_tc_kernel<NT, HILO, FOLD>;
   const size_t budget = 227 * 1024;
   const size_t misc = (sizeof(TcMisc) + 127) & ~size_t(127);
   // batch <= 4: the attention staging sits BEHIND the B chunks, so a layer's KV pages are fetched while the qkv
@@ -1425,10 +1570,10 @@ int launch_decode_tc(TcParams& P, int B, int num_sms, const TcPlanInfo& info, cu
   P.fold_in_cta = tc_fold_in_cta(B, P.hidden) ? 1 : 0;
   if (info.gu_split && !P.fold_in_cta) return set_error(NT_ERR_INVALID, "decode_tc: the flat plan needs the in-CTA fold (batch <= 4)");
   const bool hilo = B <= 8;
-  if (hilo) return launch_tc<16, true>(P, num_sms, stream);
-  if (nt == 16) return launch_tc<16, false>(P, num_sms, stream);
-  if (nt == 32) return launch_tc<32, false>(P, num_sms, stream);
-  return launch_tc<64, false>(P, num_sms, stream);
+  if (hilo) return P.fold_in_cta ? launch_tc<16, true, true>(P, num_sms, stream) : launch_tc<16, true, false>(P, num_sms, stream);
+  if (nt == 16) return launch_tc<16, false, false>(P, num_sms, stream);
+  if (nt == 32) return launch_tc<32, false, false>(P, num_sms, stream);
+  return launch_tc<64, false, false>(P, num_sms, stream);
 }
 
 }  // namespace nt

@@ -195,7 +195,12 @@ class SpeechLM:
         flat = np.concatenate([np.asarray(p, dtype=np.int64) for p in prompts])
         if flat.min() < 0 or flat.max() >= self.shape.vocab_size:
             raise ValueError("token id out of range")
-        return self.prefill_packed(torch.from_numpy(flat.astype(np.int32)), lens, sp, return_logits)
+        # stage through a persistent pinned buffer: the H2D copy of the prompt ids is asynchronous and DMA-able
+        if getattr(self, "_ids_pinned", None) is None or self._ids_pinned.numel() < flat.size:
+            self._ids_pinned = torch.empty(max(flat.size, self.max_prefill_tokens), dtype=torch.int32).pin_memory()
+        staged = self._ids_pinned[: flat.size]
+        staged.copy_(torch.from_numpy(flat.astype(np.int32)))
+        return self.prefill_packed(staged, lens, sp, return_logits)
 
     def prefill_packed(self, ids_host: torch.Tensor, lens, sp, return_logits: bool = False):
         """ids_host: int32 host tensor (pinned memory makes the H2D copy asynchronous) holding the
@@ -265,7 +270,7 @@ class SpeechLM:
     # ------------------------------------------------------------------ generation
     def generate_batch(self, prompts, eos_token_id: int, max_length: int | None = None, min_new_tokens: int = 50,
                        temperature: float = 1.0, top_k: int = 50, max_new_tokens: int | None = None, seed: int = 0,
-                       greedy: bool = False, forced: torch.Tensor | None = None, check_every: int = 32, slot_base: int = 0):
+                       greedy: bool = False, forced: torch.Tensor | None = None, check_every: int = 64, slot_base: int = 0):
         """Returns a list of int64 CPU tensors with the generated ids of each prompt (EOS included
         when it was sampled), following transformers' stopping rules (stopping_criteria.py:73-84,
         467-471): stop at EOS or when prompt + generated reaches max_length."""

@@ -61,3 +61,38 @@ def test_full_size_batch_invariance_and_reproducibility(full_lm):
     assert r < 3e-2, r
     outs = [lm.generate_batch(prompts[:2], eos, max_length=1024, min_new_tokens=4, max_new_tokens=12, seed=77) for _ in range(2)]
     assert [o.tolist() for o in outs[0]] == [o.tolist() for o in outs[1]]
+
+
+@pytest.mark.parametrize("B", [1, 3, 6])
+def test_decode_kernel_sampler_matches_standalone_sampler(full_lm, B):
+    """The persistent decode kernel samples inside the kernel (tile maxima -> candidate tiles -> exact top-k ->
+    Philox draw).  Given the logits it returns for a step, the stand-alone sampler op (``nt_op_topk_sample``, pinned
+    to the HF processors + multinomial by tests/test_gpu_kernels.py) must pick the very same token: same top-50 set,
+    same probabilities, same Philox counter (seed, slot, n_generated).  Covers the EOS mask (min_new_tokens) too."""
+    import ctypes as C
+
+    from neutts_air_b200 import _lib
+
+    lm, eos, n_steps = full_lm, 151670, 9
+    L = _lib.lib()
+    prompts = [_prompt(40 + 17 * i, 30 + i) for i in range(B)]
+    sp = lm.sampling(eos, min_new_tokens=5, max_new_tokens=16, top_k=50, temperature=0.8, seed=4242)
+    lm.prefill(prompts, sp)
+    logits = lm.decode(n_steps, sp, return_logits=True).float()            # [n_steps, B, V]; step s draws token s + 1
+    torch.cuda.synchronize()
+    toks = lm.out_tokens[:B, : n_steps + 1].cpu()
+    V = logits.shape[-1]
+    ws = torch.empty(1 << 24, dtype=torch.uint8, device=logits.device)
+    tok = torch.zeros(B, dtype=torch.int32, device=logits.device)
+    tv = torch.zeros(B, 64, device=logits.device)
+    ti = torch.zeros(B, 64, dtype=torch.int32, device=logits.device)
+    for s in range(n_steps):
+        ngen = s + 1
+        ng = torch.full((B,), ngen, dtype=torch.int32, device=logits.device)
+        row = logits[s].contiguous()
+        _lib.check(L.nt_op_topk_sample(row.data_ptr(), B, V, C.byref(sp), ng.data_ptr(), ngen, tok.data_ptr(), tv.data_ptr(),
+                                       ti.data_ptr(), ws.data_ptr(), ws.numel(), _lib.current_stream_ptr()))
+        torch.cuda.synchronize()
+        assert tok.cpu().tolist() == toks[:, ngen].tolist(), (s, tok.cpu().tolist(), toks[:, ngen].tolist())
+        if ngen < 5:
+            assert eos not in ti[:, :50].cpu().flatten().tolist()
