@@ -299,15 +299,17 @@ def decode_roofline(lm, B, lens, t_dec, n_steps, launches_per_step):
 
 
 def time_decode(lm, prompts, seed=5):
+    """(seconds, kernel launches) of the 249-step decode loop alone, CUDA events on the launching stream."""
     sp = lm.sampling(EOS, min_new_tokens=DECODE, max_new_tokens=DECODE, seed=seed)
     lm.prefill(prompts, sp)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = lm.L.nt_launch_count()
     e0.record()
     lm.decode(DECODE - 1, sp)
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / 1e3
+    return e0.elapsed_time(e1) / 1e3, lm.L.nt_launch_count() - n0
 
 
 def quick_batch(dev, B, steps=2, mixed=False, L=None):
@@ -335,13 +337,9 @@ def quick_batch(dev, B, steps=2, mixed=False, L=None):
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / 1e3 / steps
     n1 = L.nt_launch_count() if L else 0
-    m0 = L.nt_launch_count() if L else 0
-    t_dec = time_decode(lm, prompts)
-    dec_launches = ((L.nt_launch_count() - m0) if L else 0)
+    t_dec, dec_launches = time_decode(lm, prompts)
     lens = [len(p) for p in prompts]
-    # launches of the decode loop alone: subtract the prefill's (measured separately below would cost a pass; the
-    # persistent kernel is exactly one launch, the chain reports its graph size)
-    per_step = None if B <= 8 else max(1, round(dec_launches / DECODE))
+    per_step = None if dec_launches <= 2 else max(1, round(dec_launches / (DECODE - 1)))   # persistent kernel: one launch
     out = {"per_gpu_batch": B, "workload": ("configs[2]: mixed-length prompts U{200..1400} (mean %.0f)" % (sum(lens) / B)) if mixed else "configs[1] shape, 500-token prompts",
            "value": AUDIO_S * B / t, "unit": "audio-s/s", "ms_per_step": t * 1e3, "steps": steps,
            "decode_tok_s": B * (DECODE - 1) / t_dec, "decode_ms_per_token_step": t_dec / (DECODE - 1) * 1e3,
@@ -431,18 +429,14 @@ def main_b200(args):
     clk = clocks.stop() if rank == 0 else None
 
     # the parts, each timed alone with CUDA events
-    m0 = L.nt_launch_count()
-    t_dec = time_decode(lm, prompts)
-    dec_launches = L.nt_launch_count() - m0
+    t_dec, dec_launches = time_decode(lm, prompts)
     sp = lm.sampling(EOS, min_new_tokens=DECODE, max_new_tokens=DECODE, seed=5)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    m1 = L.nt_launch_count()
     e0.record()
     lm.prefill(prompts, sp)
     e1.record()
     torch.cuda.synchronize()
     t_pre = e0.elapsed_time(e1) / 1e3
-    pre_launches = L.nt_launch_count() - m1
     e0.record()
     codec.decode_code(codes_from(lm))
     e1.record()
@@ -468,8 +462,7 @@ def main_b200(args):
             td.destroy_process_group()
         return
     total_audio = AUDIO_S * B * world * args.steps
-    n_dec_launch = dec_launches - pre_launches            # time_decode = one prefill + the decode loop
-    per_step = None if n_dec_launch <= 2 else max(1, round(n_dec_launch / (DECODE - 1)))
+    per_step = None if dec_launches <= 2 else max(1, round(dec_launches / (DECODE - 1)))   # persistent kernel: one launch
     roof = decode_roofline(lm, B, lens, t_dec, DECODE - 1, per_step)
     roof["share_of_timed_region"] = t_dec / (t_dev / args.steps)
     line = {

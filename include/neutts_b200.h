@@ -42,7 +42,7 @@ typedef enum {
 
 const char* nt_last_error(void);
 /* library/ABI version, bumped on any signature change */
-int nt_abi_version(void);   /* 2: nt_sampling gained limits + slot_base */
+int nt_abi_version(void);   /* 2: nt_sampling gained limits + slot_base; 3: nt_codec_config.precision */
 /* number of kernels launched by this library since load (all streams); bench.py reports the delta */
 uint64_t nt_launch_count(void);
 
@@ -184,6 +184,11 @@ typedef struct {
   float norm_eps, rope_base, mag_clip;
   int rope_time_axis;                   /* 1: rotary over frames; 0: upstream quirk (no-op, skipped) */
   int max_batch, max_frames;
+  int precision;                        /* GEMM arithmetic on the tensor cores (fp32 storage, fp32 accumulate):
+                                           0 = TF32, and 3xTF32 (hi/lo split, ~fp32 products) for the ISTFT head and the
+                                               inverse-DFT GEMMs, whose outputs go through exp / sin / cos   [default]
+                                           1 = TF32 everywhere (fastest)
+                                           2 = 3xTF32 everywhere (fp32-grade; ~2.5x the codec time) */
 } nt_codec_config;
 
 /* All f32, device.  Conv weights are pre-flattened tap-major: [C_out, k*C_in] with

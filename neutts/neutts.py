@@ -425,7 +425,7 @@ class NeuTTS:
             need = min(F + LA - (int(hlen_h[b]) - n_dec[b]) for b in range(B) if not finished[b])
             room = min(limits[b] - int(ngen_h[b]) for b in range(B) if not finished[b])
             steps = max(1, min(need, room))
-            lo = int(ngen_h.min())
+            lo = min(int(ngen_h[b]) for b in range(B) if not finished[b])   # finished slots were absorbed completely above
             lm.decode(steps, sp)
             hi = int(ngen_h.max()) + steps
 

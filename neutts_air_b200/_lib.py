@@ -66,7 +66,7 @@ class CodecConfig(C.Structure):
         ("mlp_hidden", C.c_int), ("groups", C.c_int), ("embed_kernel", C.c_int),
         ("n_fft", C.c_int), ("hop", C.c_int), ("fsq_levels", C.c_int), ("fsq_dims", C.c_int),
         ("norm_eps", C.c_float), ("rope_base", C.c_float), ("mag_clip", C.c_float),
-        ("rope_time_axis", C.c_int), ("max_batch", C.c_int), ("max_frames", C.c_int),
+        ("rope_time_axis", C.c_int), ("max_batch", C.c_int), ("max_frames", C.c_int), ("precision", C.c_int),
     ]
 
 

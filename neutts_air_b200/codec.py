@@ -78,7 +78,14 @@ def pack_weights(shape: CodecShape, w: dict, device) -> dict:
 
 
 class CodecDecoder:
-    def __init__(self, shape: CodecShape, weights: dict, device="cuda", max_batch: int = 1, max_frames: int = 2048):
+    PRECISIONS = {"default": 0, "tf32": 1, "3xtf32": 2}
+
+    def __init__(self, shape: CodecShape, weights: dict, device="cuda", max_batch: int = 1, max_frames: int = 2048,
+                 precision: str = "default"):
+        """``precision``: "default" = TF32 tensor-core GEMMs with 3xTF32 (fp32-grade) ISTFT-head and inverse-DFT GEMMs,
+        "tf32" = TF32 everywhere, "3xtf32" = fp32-grade everywhere (see ``nt_codec_config.precision``)."""
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(self.PRECISIONS)}")
         if not torch.cuda.is_available():
             raise RuntimeError("neutts_air_b200.CodecDecoder needs a CUDA device (sm_100a); there is no CPU fallback")
         if shape.rope_axis not in ("time", "head"):
@@ -92,7 +99,7 @@ class CodecDecoder:
             cfg = _lib.CodecConfig(shape.hidden, shape.depth, shape.heads, shape.head_dim, shape.mlp_mult * shape.hidden,
                                    shape.groups, shape.embed_kernel, shape.n_fft, shape.hop, shape.fsq_levels,
                                    shape.fsq_dims, shape.norm_eps, shape.rope_base, shape.mag_clip,
-                                   1 if shape.rope_axis == "time" else 0, max_batch, max_frames)
+                                   1 if shape.rope_axis == "time" else 0, max_batch, max_frames, self.PRECISIONS[precision])
             ws_bytes = self.L.nt_codec_workspace_bytes(C.byref(cfg))
             if ws_bytes == 0:
                 _lib.check(-1)

@@ -253,9 +253,28 @@ __global__ void __launch_bounds__(256) ola_kernel(const float* frames, int N, in
   pcm[static_cast<long long>(b) * total + n] = acc / env;
 }
 
+// 3xTF32 operand split: hi = x rounded to the 10-bit TF32 mantissa (exactly representable, so the tensor core's own
+// fp32 -> tf32 conversion leaves it alone), lo = x - hi (exact in fp32).  A.W ~ A_lo.W_hi + A_hi.W_lo + A_hi.W_hi with
+// fp32 accumulation is accurate to ~2^-21 per product instead of 2^-11.
+__global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = x[i];
+    const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
 }  // namespace nt
 
 using namespace nt;
+
+struct SplitW {   // hi / lo halves of one weight matrix (workspace), null when the matrix runs in plain TF32
+  float* hi = nullptr;
+  float* lo = nullptr;
+};
 
 struct nt_codec {
   nt_codec_config cfg;
@@ -263,6 +282,10 @@ struct nt_codec {
   std::vector<const float*> rn[8], blk[6];
   float *x0, *x1, *x2, *x3, *xn, *qkv, *hbuf, *att, *sp, *fr, *inv_freq;
   int kpad;
+  // 3xTF32 (cfg.precision != 1): split weights, split-activation scratch, partial-sum scratch
+  SplitW s_head, s_idft, s_embed;
+  std::vector<SplitW> s_rn[2], s_blk[4];   // resnet conv1 / conv2; wqkv, wproj, fc1, fc2
+  float *a_hi = nullptr, *a_lo = nullptr, *acc = nullptr;
 };
 
 static int codec_check(const nt_codec_config* c) {
@@ -274,6 +297,7 @@ static int codec_check(const nt_codec_config* c) {
   if (c->fsq_dims > 16 || c->fsq_levels < 2) return set_error(NT_ERR_INVALID, "codec: unsupported FSQ shape");
   if (c->n_fft % 4 || c->hop < 1 || (c->n_fft - c->hop) % 2 || c->n_fft < c->hop) return set_error(NT_ERR_INVALID, "codec: unsupported STFT geometry");
   if (c->max_batch < 1 || c->max_frames < 1) return set_error(NT_ERR_INVALID, "codec: bad sizes");
+  if (c->precision < 0 || c->precision > 2) return set_error(NT_ERR_INVALID, "codec: precision %d not in 0..2", c->precision);
   return NT_OK;
 }
 
@@ -293,6 +317,31 @@ static size_t codec_carve(const nt_codec_config& c, void* ws, size_t bytes, nt_c
   k->sp = a.take<float>(rows * kpad);
   k->fr = a.take<float>(rows * c.n_fft);
   k->inv_freq = a.take<float>(64);
+  if (c.precision != 1) {
+    const size_t C = c.hidden, nb2 = size_t(c.n_fft) + 2;
+    auto takew = [&](SplitW& w, size_t n) { w.hi = a.take<float>(n), w.lo = a.take<float>(n); };
+    takew(k->s_head, nb2 * C);
+    takew(k->s_idft, size_t(c.n_fft) * kpad);
+    size_t widest = kpad > c.n_fft ? kpad : c.n_fft;
+    if (c.precision == 2) {
+      takew(k->s_embed, C * c.embed_kernel * C);
+      for (int i = 0; i < 2; ++i) {
+        k->s_rn[i].assign(4, SplitW());
+        for (int j = 0; j < 4; ++j) takew(k->s_rn[i][j], C * 3 * C);
+      }
+      const size_t bn[4] = {3 * C * C, C * C, size_t(c.mlp_hidden) * C, C * size_t(c.mlp_hidden)};
+      for (int i = 0; i < 4; ++i) {
+        k->s_blk[i].assign(c.depth, SplitW());
+        for (int j = 0; j < c.depth; ++j) takew(k->s_blk[i][j], bn[i]);
+      }
+      if (size_t(c.mlp_hidden) > widest) widest = c.mlp_hidden;
+      if (3 * C > widest) widest = 3 * C;
+    }
+    if (C > widest) widest = C;
+    k->a_hi = a.take<float>(rows * widest);
+    k->a_lo = a.take<float>(rows * widest);
+    k->acc = a.take<float>(rows * widest);
+  }
   return a.off;
 }
 
@@ -334,6 +383,26 @@ extern "C" int nt_codec_create(const nt_codec_config* cfg, const nt_codec_weight
     delete k;
     return set_error(NT_ERR_CUDA, "codec workspace initialisation failed");
   }
+  if (cfg->precision != 1) {   // split the weights of the 3xTF32 GEMMs once
+    const size_t C = cfg->hidden;
+    auto splitw = [&](const float* src, const SplitW& w, size_t n) {
+      if (w.hi) split_tf32_kernel<<<592, 256>>>(src, w.hi, w.lo, static_cast<long long>(n));
+    };
+    splitw(w->head_w, k->s_head, (size_t(cfg->n_fft) + 2) * C);
+    splitw(w->idft_basis, k->s_idft, size_t(cfg->n_fft) * k->kpad);
+    if (cfg->precision == 2) {
+      splitw(w->embed_w, k->s_embed, C * cfg->embed_kernel * C);
+      for (int j = 0; j < 4; ++j) splitw(k->rn[2][j], k->s_rn[0][j], C * 3 * C), splitw(k->rn[6][j], k->s_rn[1][j], C * 3 * C);
+      const size_t bn[4] = {3 * C * C, C * C, size_t(cfg->mlp_hidden) * C, C * size_t(cfg->mlp_hidden)};
+      const int bi[4] = {1, 2, 4, 5};
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < cfg->depth; ++j) splitw(k->blk[bi[i]][j], k->s_blk[i][j], bn[i]);
+    }
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+      delete k;
+      return set_error(NT_ERR_CUDA, "codec: weight split failed");
+    }
+  }
   *out = k;
   return NT_OK;
 }
@@ -351,17 +420,32 @@ struct CodecRun {
 
   // masked GEMM on the padded layout: out rows r+3 for r with (r % Tp) < N.
   // A points at the first row the tap window of output row 0 touches.
+  // sw (optional): the weight's hi / lo halves -> 3xTF32: acc = residual + A_lo.W_hi; acc += A_hi.W_lo;
+  // out = act(bias + acc + A_hi.W_hi) (small terms first; bias / activation only in the last pass).
   int gemm(const float* A, int K, int lda, const float* W, const float* bias, const float* residual, nt_act act, float* out,
-           int ldc, int Nout, bool masked) {
+           int ldc, int Nout, bool masked, const SplitW* sw = nullptr, int ldw = 0) {
     nt_gemm_args a;
     memset(&a, 0, sizeof(a));
     a.dtype = NT_TF32;
     a.M = masked ? rows - 6 : rows;
-    a.N = Nout, a.K = K, a.A = A, a.lda = lda, a.W = W, a.ldw = K;
+    a.N = Nout, a.K = K, a.A = A, a.lda = lda, a.W = W, a.ldw = ldw ? ldw : K;
     a.bias = bias, a.residual = residual, a.ldr = ldc, a.act = act, a.out_f32 = out, a.ldc = ldc;
     if (masked) a.valid_period = Tp, a.valid_len = N;
+    if (!sw || !sw->hi) return gemm_dispatch(a, s, nullptr, true);
+    const long long a_elems = static_cast<long long>(a.M + (K + lda - 1) / lda - 1) * lda;   // rows the tap window touches
+    const int lda_acc = (Nout + 3) & ~3;
+    int rc = launch_kernel(split_tf32_kernel, dim3(296), dim3(256), 0, s, true, A, k->a_hi, k->a_lo, a_elems);
+    if (rc) return rc;
+    nt_gemm_args p = a;
+    p.bias = nullptr, p.act = NT_ACT_NONE, p.out_f32 = k->acc, p.ldc = lda_acc;
+    p.A = k->a_lo, p.W = sw->hi;                                     // pass 1: acc = residual + A_lo.W_hi
+    if ((rc = gemm_dispatch(p, s, nullptr, true))) return rc;
+    p.A = k->a_hi, p.W = sw->lo, p.residual = k->acc, p.ldr = lda_acc;  // pass 2: acc += A_hi.W_lo
+    if ((rc = gemm_dispatch(p, s, nullptr, true))) return rc;
+    a.A = k->a_hi, a.W = sw->hi, a.residual = k->acc, a.ldr = lda_acc;  // pass 3: out = act(bias + acc + A_hi.W_hi)
     return gemm_dispatch(a, s, nullptr, true);
   }
+  const SplitW* sp(const std::vector<SplitW>& v, int i) const { return v.empty() ? nullptr : &v[i]; }
   int resnet(int idx) {
     const nt_codec_config& c = k->cfg;
     const int cpg = C / c.groups;
@@ -369,11 +453,12 @@ struct CodecRun {
     if ((rc = launch_kernel(groupnorm_swish_kernel, dim3(c.groups, B), dim3(256), 0, s, true, (const float*)k->x1, N, Tp, C, cpg,
                             c.norm_eps, k->rn[0][idx], k->rn[1][idx], k->x2)))
       return rc;
-    if ((rc = gemm(k->x2 + 2 * C, 3 * C, C, k->rn[2][idx], k->rn[3][idx], nullptr, NT_ACT_NONE, k->x3 + 3 * C, C, C, true))) return rc;
+    if ((rc = gemm(k->x2 + 2 * C, 3 * C, C, k->rn[2][idx], k->rn[3][idx], nullptr, NT_ACT_NONE, k->x3 + 3 * C, C, C, true, sp(k->s_rn[0], idx))))
+      return rc;
     if ((rc = launch_kernel(groupnorm_swish_kernel, dim3(c.groups, B), dim3(256), 0, s, true, (const float*)k->x3, N, Tp, C, cpg,
                             c.norm_eps, k->rn[4][idx], k->rn[5][idx], k->x2)))
       return rc;
-    return gemm(k->x2 + 2 * C, 3 * C, C, k->rn[6][idx], k->rn[7][idx], k->x1 + 3 * C, NT_ACT_NONE, k->x1 + 3 * C, C, C, true);
+    return gemm(k->x2 + 2 * C, 3 * C, C, k->rn[6][idx], k->rn[7][idx], k->x1 + 3 * C, NT_ACT_NONE, k->x1 + 3 * C, C, C, true, sp(k->s_rn[1], idx));
   }
 };
 }  // namespace
@@ -397,7 +482,7 @@ extern "C" int nt_codec_decode(nt_codec* k, const int32_t* codes, int B, int N, 
                           k->w.fsq_w, k->w.fsq_b, k->x0)))
     return rc;
   // B3: Conv1d k=7 pad=3
-  if ((rc = r.gemm(k->x0, 7 * C, C, k->w.embed_w, k->w.embed_b, nullptr, NT_ACT_NONE, k->x1 + 3 * C, C, C, true))) return rc;
+  if ((rc = r.gemm(k->x0, 7 * C, C, k->w.embed_w, k->w.embed_b, nullptr, NT_ACT_NONE, k->x1 + 3 * C, C, C, true, &k->s_embed))) return rc;
   // B4: prior_net
   for (int i = 0; i < 2; ++i)
     if ((rc = r.resnet(i))) return rc;
@@ -407,20 +492,22 @@ extern "C" int nt_codec_decode(nt_codec* k, const int32_t* codes, int B, int N, 
     if ((rc = launch_kernel(rownorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, true, (const float*)k->x1, rows, C, c.norm_eps,
                             k->blk[0][l], (const float*)nullptr, 0, k->xn)))
       return rc;
-    if ((rc = r.gemm(k->xn, C, C, k->blk[1][l], nullptr, nullptr, NT_ACT_NONE, k->qkv, 3 * C, 3 * C, false))) return rc;
+    if ((rc = r.gemm(k->xn, C, C, k->blk[1][l], nullptr, nullptr, NT_ACT_NONE, k->qkv, 3 * C, 3 * C, false, r.sp(k->s_blk[0], l)))) return rc;
     if (c.rope_time_axis)
       if ((rc = launch_kernel(codec_rope_kernel, dim3(B * N), dim3(256), 0, s, true, k->qkv, N, Tp, C, c.heads, (const float*)k->inv_freq)))
         return rc;
     if ((rc = launch_kernel(codec_attn_kernel, dim3((N + 127) / 128, c.heads, B), dim3(128), 0, s, true, (const float*)k->qkv, N, Tp, C,
                             scale_log2, k->att)))
       return rc;
-    if ((rc = r.gemm(k->att + 3 * C, C, C, k->blk[2][l], nullptr, k->x1 + 3 * C, NT_ACT_NONE, k->x1 + 3 * C, C, C, true))) return rc;
+    if ((rc = r.gemm(k->att + 3 * C, C, C, k->blk[2][l], nullptr, k->x1 + 3 * C, NT_ACT_NONE, k->x1 + 3 * C, C, C, true, r.sp(k->s_blk[1], l))))
+      return rc;
     if ((rc = launch_kernel(rownorm_kernel, dim3((rows + 7) / 8), dim3(256), 0, s, true, (const float*)k->x1, rows, C, c.norm_eps,
                             k->blk[3][l], (const float*)nullptr, 0, k->xn)))
       return rc;
-    if ((rc = r.gemm(k->xn, C, C, k->blk[4][l], nullptr, nullptr, NT_ACT_SILU, k->hbuf, c.mlp_hidden, c.mlp_hidden, false))) return rc;
+    if ((rc = r.gemm(k->xn, C, C, k->blk[4][l], nullptr, nullptr, NT_ACT_SILU, k->hbuf, c.mlp_hidden, c.mlp_hidden, false, r.sp(k->s_blk[2], l))))
+      return rc;
     if ((rc = r.gemm(k->hbuf + 3 * size_t(c.mlp_hidden), c.mlp_hidden, c.mlp_hidden, k->blk[5][l], nullptr, k->x1 + 3 * C, NT_ACT_NONE,
-                     k->x1 + 3 * C, C, C, true)))
+                     k->x1 + 3 * C, C, C, true, r.sp(k->s_blk[3], l))))
       return rc;
   }
   // post_net
@@ -431,15 +518,9 @@ extern "C" int nt_codec_decode(nt_codec* k, const int32_t* codes, int B, int N, 
                           k->w.final_ln_w, k->w.final_ln_b, 1, k->xn)))
     return rc;
   const int nb = c.n_fft / 2 + 1, kp = k->kpad;
-  if ((rc = r.gemm(k->xn, C, C, k->w.head_w, k->w.head_b, nullptr, NT_ACT_NONE, k->sp, kp, 2 * nb, false))) return rc;
+  if ((rc = r.gemm(k->xn, C, C, k->w.head_w, k->w.head_b, nullptr, NT_ACT_NONE, k->sp, kp, 2 * nb, false, &k->s_head))) return rc;
   if ((rc = launch_kernel(spec_kernel, dim3(rows), dim3(256), 0, s, true, k->sp, (long long)kp, nb, c.mag_clip))) return rc;
   // B7: inverse rDFT (windowed basis) as a GEMM, then overlap-add
-  {
-    nt_gemm_args a;
-    memset(&a, 0, sizeof(a));
-    a.dtype = NT_TF32, a.M = rows, a.N = c.n_fft, a.K = 2 * nb, a.A = k->sp, a.lda = kp, a.W = k->w.idft_basis, a.ldw = kp;
-    a.out_f32 = k->fr, a.ldc = c.n_fft;
-    if ((rc = gemm_dispatch(a, s, nullptr, true))) return rc;
-  }
+  if ((rc = r.gemm(k->sp, 2 * nb, kp, k->w.idft_basis, nullptr, nullptr, NT_ACT_NONE, k->fr, c.n_fft, c.n_fft, false, &k->s_idft, kp))) return rc;
   return launch_kernel(ola_kernel, dim3((c.hop * N + 255) / 256, B), dim3(256), 0, s, true, (const float*)k->fr, N, Tp, c.n_fft, c.hop, pcm);
 }

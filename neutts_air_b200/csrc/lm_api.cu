@@ -186,7 +186,7 @@ static int lm_check_config(const nt_lm_config* c) {
 }
 
 extern "C" const char* nt_last_error(void) { return g_err; }
-extern "C" int nt_abi_version(void) { return 2; }
+extern "C" int nt_abi_version(void) { return 3; }
 extern "C" uint64_t nt_launch_count(void) { return g_launches.load(); }
 
 extern "C" size_t nt_lm_workspace_bytes(const nt_lm_config* cfg) {
@@ -574,9 +574,9 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
   // NT_DECODE_IMPL = tc (default: persistent tcgen05 kernel, every batch size) | mega | perop (round-1 paths, kept
   // for A/B measurements and as the fallback for shapes the tcgen05 plan does not take)
   const char* impl = getenv("NT_DECODE_IMPL");
-  // default: the tcgen05 kernel up to NT_TC_MAX_BATCH sequences (measured on B200: 1.03 ms / step at batch 8 against
-  // 1.23 ms for the per-op chain; from batch 16 the chain's step time (1.25 - 1.31 ms, flat in the batch) wins)
-  int tc_cap = 8;
+  // default: the tcgen05 kernel up to NT_TC_MAX_BATCH sequences (measured on B200, ms / step: 0.72 / 0.83 / 0.90 / 1.03
+  // at batch 1 / 4 / 8 / 16, then 1.35 / 2.04 at 32 / 64, where the per-op chain's 1.25 - 1.31 ms (flat in the batch) wins)
+  int tc_cap = 16;
   if (const char* e = getenv("NT_TC_MAX_BATCH")) tc_cap = atoi(e);
   const bool want_tc = (impl && impl[0] == 't') || ((!impl || !impl[0]) && B <= tc_cap);
   const int tc_layers = lm->debug_layers >= 0 ? lm->debug_layers : c.n_layers;

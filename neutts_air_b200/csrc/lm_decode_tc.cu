@@ -1417,8 +1417,12 @@ static size_t tc_chunk_bytes(int nt) {   // B chunks (+ fold_in_cta: fp32 rows a
 static size_t tc_attn_bytes(int aw) { return (tc_attn_layout_bytes(aw) + 1023) & ~size_t(1023); }
 
 bool tc_fold_in_cta(int B, int hidden) {
-  const char* fe = getenv("NT_TC_FOLD");   // experiments: "phase" forces the fold phases at small batch
-  return B <= 4 && size_t(B) * hidden * 4 <= 16 * 1024 && hidden <= 1024 && !(fe && fe[0] == 'p');
+  // Measured on B200 (us / step, NeuTTS-Air): in-CTA fold 719 / 916 / 1111 / 1283 at batch 1 / 2 / 3 / 4, fold phases
+  // 806 / 805 / 826 / 830: every consumer re-folding ALL rows stops paying at two sequences.
+  // NT_TC_FOLD: "phase" forces the fold phases at batch 1, "cta" the in-CTA fold up to batch 4 (experiments).
+  const char* fe = getenv("NT_TC_FOLD");
+  const int cap = (fe && fe[0] == 'c') ? 4 : 1;
+  return B <= cap && size_t(B) * hidden * 4 <= 16 * 1024 && hidden <= 1024 && !(fe && fe[0] == 'p');
 }
 
 int tc_build_plan(const TcShape& s, int G, bool flat, TcPlan* plan, unsigned char* gu_nsl, TcPlanInfo* info) {

@@ -26,7 +26,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/neutts_b200.h but not exported"
     assert sorted(_lib.EXPORTS) == names            # the ctypes binding covers exactly the header
-    assert L.nt_abi_version() == 2
+    assert L.nt_abi_version() == 3
 
 
 def test_workspace_queries_and_validation():

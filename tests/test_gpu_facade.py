@@ -83,3 +83,48 @@ def test_facade_streaming_geometry():
     plan = SO.chunk_plan(len(ref_codes), len(ref_codes) + n_frames, hop=hop)
     full = [c for c in chunks[:-1]] if len(plan) > 1 else []
     assert all(len(c) == tts.streaming_stride_samples for c in full)   # every non-final chunk is 25 frames
+
+
+@pytest.mark.parametrize("B,F", [(1, 25), (3, 25), (3, 50)])
+def test_streamed_pcm_equals_windowed_oracle_decode(B, F):
+    """the streamed AUDIO, not just the chunk geometry.  The tokens the engine generated are read
+    back after the stream; the CPU oracles then redo what the reference does with them (``neutts/neutts.py:401-465``):
+    every planned window through the codec oracle, slice, triangular overlap-add (oracle/stream_oracle.py).  The
+    streamed PCM must match within the codec's own parity bar.  B = 3 runs ``infer_stream_batch`` (configs[4] shape:
+    lock-step decode, windows gathered on the device, shared codec calls); F = 50 is "codec every 50 tokens"."""
+    tts, ccfg = _tts(max_batch=B, seed=11)
+    cw = CO.random_weights(ccfg, 2)
+    hop = ccfg.hop
+    tts.hop_length = hop
+    tts.streaming_frames_per_chunk = F
+    tts.streaming_stride_samples = F * hop
+    refs = [list(range(60 + 9 * b, 120 + 20 * b)) for b in range(B)]
+    texts = ["streaming test sentence number %d" % b for b in range(B)]
+    got = [[] for _ in range(B)]
+    if B == 1:
+        got[0] = list(tts.infer_stream(texts[0], refs[0], "reference"))
+    else:
+        for out in tts.infer_stream_batch(texts, refs, ["reference"] * B):
+            for b, o in enumerate(out):
+                if o is not None:
+                    got[b].append(o)
+    lm = tts.backbone
+    ngen = lm.n_generated[:B].cpu().tolist()
+    assert min(ngen) >= 50                                   # min_new_tokens of the reference sampling setup
+    for b in range(B):
+        gen = tts._ids_to_codes(lm.out_tokens[b, : ngen[b]].cpu()).tolist()
+        allc = refs[b] + gen
+        frames = []
+        for (t0, t1, s0, s1) in SO.chunk_plan(len(refs[b]), len(allc), hop=hop, frames=F):
+            with torch.no_grad():
+                wav = CO.decode_code(torch.tensor(allc[t0:t1])[None, None, :], cw, ccfg)[0, 0].numpy()
+            frames.append(wav[s0:s1] if s1 is not None else wav[max(s0, 0):])
+        have = np.concatenate(got[b]) if got[b] else np.zeros(0, np.float32)
+        if not frames:
+            assert have.size == 0
+            continue
+        want = SO.linear_overlap_add(frames, F * hop)
+        assert have.shape == want.shape, (b, have.shape, want.shape, len(gen))
+        err = float(np.sqrt(np.mean((have - want) ** 2)) / max(np.sqrt(np.mean(want ** 2)), 1e-9))
+        print(f"STREAM-PCM-PARITY B={B} F={F} slot {b}: {len(gen)} generated frames, {len(frames)} windows, relRMS {err:.2e}")
+        assert err < 5e-3, (b, err)

@@ -459,3 +459,105 @@ def test_generate_batch_caps_are_per_sequence():
     assert list(kw["limits"]) == [548, 1748]  # ... and every slot carries its own cap (2048 - prompt length)
     lm.generate_batch([[1] * 300, [2] * 300], eos_token_id=9, max_length=2048, check_every=4096)
     assert calls["sampling"][1]["limits"] is None and calls["sampling"][0][2] == 1748
+
+
+class FakeBatchStreamLM:
+    """Batched prefill()/decode() surface of SpeechLM: one scripted token stream per slot, lock-step decoding,
+    finished slots idle (as inside the persistent kernel)."""
+    device = torch.device("cpu")
+
+    def __init__(self, scripts, max_new=4096):
+        self.scripts, self.max_new = [list(s) for s in scripts], max_new
+        B = len(scripts)
+        self.out_tokens = torch.zeros(B, max_new, dtype=torch.int32)
+        self.n_generated = torch.zeros(B, dtype=torch.int32)
+        self.done = torch.zeros(B, dtype=torch.int32)
+        self.decode_calls = []
+
+    def sampling(self, eos, min_new, max_new, top_k, temperature, seed, limits=None):
+        self.eos = eos
+        self.limits = list(limits) if limits is not None else [max_new] * len(self.scripts)
+        return None
+
+    def _emit(self):
+        for b, script in enumerate(self.scripts):
+            n = int(self.n_generated[b])
+            if int(self.done[b]) or n >= self.limits[b]:
+                continue
+            tok = script[n] if n < len(script) else self.eos
+            self.out_tokens[b, n] = tok
+            self.n_generated[b] = n + 1
+            if tok == self.eos or n + 1 >= self.limits[b]:
+                self.done[b] = 1
+
+    def prefill(self, prompts, sp):
+        self._emit()
+
+    def decode(self, steps, sp):
+        assert steps >= 1
+        self.decode_calls.append(steps)
+        for _ in range(steps):
+            self._emit()
+
+
+class BatchRampCodec(RampCodec):
+    max_batch = 2          # smaller than the batch: same-length windows are split over several codec calls
+
+    def decode_code(self, codes):
+        assert codes.shape[0] <= self.max_batch
+        return torch.cat([RampCodec.decode_code(self, codes[r: r + 1]) for r in range(codes.shape[0])])
+
+
+@pytest.mark.parametrize("frames_per_chunk", [25, 50])
+def test_stream_batch_matches_reference_window_plan_per_utterance(frames_per_chunk):
+    """infer_stream_batch (BASELINE configs[4]: batch-8 streaming; 50 = "codec every 50 tokens"): every utterance of
+    the batch gets exactly the audio the single-utterance reference procedure gives it -- different reference
+    lengths, generated lengths (one ends after 9 tokens, one runs 3x longer), junk ids, one slot stopped by its
+    own max_length -- while the slots decode in lock-step and share codec calls."""
+    tts, tok = _tts()
+    codec = BatchRampCodec()
+    hop = codec.hop
+    tts.codec, tts.hop_length = codec, hop
+    tts.streaming_frames_per_chunk = frames_per_chunk
+    tts.streaming_stride_samples = frames_per_chunk * hop
+    rng = np.random.default_rng(77)
+    n_gens, n_refs, junk = [143, 9, 400, 61, 230], [60, 75, 52, 120, 60], [0, 0, 5, 3, 0]
+    refs = [rng.integers(0, 65536, n).tolist() for n in n_refs]
+    scripts, kept = [], []
+    for n, j in zip(n_gens, junk):
+        codes = rng.integers(0, 65536, n).tolist()
+        sc = []
+        for i, c in enumerate(codes):
+            if j and i % j == 0:
+                sc.append(65)
+            sc.append(tok.speech_base + c)
+        scripts.append(sc)
+        kept.append(codes)
+    lm = FakeBatchStreamLM(scripts)
+    tts.backbone = lm
+    # slot 2 is cut by max_length: the facade caps it at max_context - len(prompt)
+    prompt_lens = [len(tts._apply_chat_template(r, "ref", "hello")) for r in refs]
+    tts.max_context = prompt_lens[2] + 301
+    lim2 = 301
+    kept[2] = [t - tok.speech_base for t in scripts[2][:lim2] if t >= tok.speech_base]
+    got = [[] for _ in refs]
+    n_yields = 0
+    for out in tts.infer_stream_batch(["hello"] * 5, refs, ["ref"] * 5):
+        assert len(out) == 5 and any(o is not None for o in out)
+        n_yields += 1
+        for b, o in enumerate(out):
+            if o is not None:
+                got[b].append(o)
+    assert int(lm.n_generated[2]) == lim2
+    for b in range(5):
+        allc = refs[b] + kept[b]
+        frames = []
+        for (t0, t1, s0, s1) in SO.chunk_plan(len(refs[b]), len(allc), hop=hop, frames=frames_per_chunk):
+            wav = RampCodec.decode_code(codec, torch.tensor(allc[t0:t1])[None, None, :])[0, 0].numpy()
+            frames.append(wav[s0:s1] if s1 is not None else wav[max(s0, 0):])
+        want = SO.linear_overlap_add(frames, tts.streaming_stride_samples) if frames else np.zeros(0, np.float32)
+        have = np.concatenate(got[b]) if got[b] else np.zeros(0, np.float32)
+        assert have.shape == want.shape, (b, have.shape, want.shape)
+        assert np.abs(have - want).max() < 1e-5, b
+    assert max(lm.decode_calls) <= frames_per_chunk + tts.streaming_lookforward
+    assert n_yields < sum(len(g) for g in got)          # rounds are shared between the utterances
