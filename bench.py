@@ -268,6 +268,9 @@ def make_facade(lm, codec, batch, seed):
         def _ids_to_codes(self, ids):
             return (ids.long() - SPEECH_BASE) % 65536
 
+        def _ids_to_codes_masked(self, ids):
+            return (ids.long() - SPEECH_BASE) % 65536, torch.ones_like(ids, dtype=torch.bool)
+
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         return BenchTTS(backbone=lm, codec=codec, tokenizer=_BenchTokenizer(), phonemizer=object(), max_batch=batch, seed=seed)
@@ -348,6 +351,52 @@ def quick_batch(dev, B, steps=2, mixed=False, L=None):
     del lm, codec
     torch.cuda.empty_cache()
     return out
+
+
+def stream_line(dev, B=8, frames_per_chunk=50, L=None):
+    """configs[4]: NeuTTS-Nano-shaped LM, batch-8 STREAMING synthesis through neutts.NeuTTS (infer_stream_batch's
+    engine loop), the codec invoked every 50 generated tokens on the reference's window geometry (lookback 50,
+    lookahead 5, overlap 1).  Nano's architecture is not published offline: the shape is inferred from
+    the README's ~229 M total / ~120 M active parameters (hidden 512 from the embedding share)."""
+    from neutts_air_b200 import synthetic
+    from neutts_air_b200.codec import CodecDecoder, CodecShape
+    from neutts_air_b200.lm import LMShape, SpeechLM
+
+    shape = LMShape(vocab_size=217472, hidden_size=512, intermediate_size=2048, num_layers=28, num_heads=8, num_kv_heads=2)
+    lm = SpeechLM(shape, synthetic.lm_state_dict(shape, 1), device=dev, max_batch=B, max_ctx=2048, max_new=256, max_prefill_tokens=B * PREFILL)
+    if "codec" not in _WEIGHTS:
+        _WEIGHTS["codec"] = synthetic.codec_weights(CodecShape(), 0)
+    codec = CodecDecoder(CodecShape(), _WEIGHTS["codec"], device=dev, max_batch=B, max_frames=256)
+    tts = make_facade(lm, codec, B, seed=99)
+    tts.streaming_frames_per_chunk = frames_per_chunk
+    tts.streaming_stride_samples = frames_per_chunk * HOP
+    prompts = synth_prompts(B, 217472, SPEECH_BASE, 777)
+    refs = [[t - SPEECH_BASE for t in p[PREFILL - 372:]] for p in prompts]      # the reference-voice codes inside the prompt
+
+    def run():
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        first, samples, rounds = None, 0, 0
+        for out in tts._stream_batch(prompts, refs):
+            rounds += 1
+            n = sum(len(o) for o in out if o is not None)
+            if n and first is None:
+                first = time.perf_counter() - t0
+            samples += n
+        return time.perf_counter() - t0, first, samples, rounds
+
+    run()
+    n0 = L.nt_launch_count() if L else 0
+    t, first, samples, rounds = run()
+    launches = (L.nt_launch_count() - n0) if L else None
+    ngen = int(lm.n_generated[:B].sum())
+    del lm, codec, tts
+    torch.cuda.empty_cache()
+    return {"workload": f"configs[4]: NeuTTS-Nano-like LM (hidden 512, 28 layers, 8/2 heads, inter 2048; inferred), batch={B} streaming, "
+                        f"500-token prompts, codec every {frames_per_chunk} tokens (window {frames_per_chunk}+50+5+1 frames)",
+            "per_gpu_batch": B, "value": samples / SR / t, "unit": "audio-s/s", "ms_total": t * 1e3, "first_chunk_ms": first * 1e3 if first else None,
+            "audio_s": samples / SR, "generated_tokens": ngen, "decode_tok_s": ngen / t, "rounds": rounds, "gpu_launches": launches,
+            "api": "neutts.NeuTTS._stream_batch (engine loop of infer_stream_batch)"}
 
 
 def main_b200(args):
@@ -490,7 +539,7 @@ def main_b200(args):
         del lm, codec, tts
         torch.cuda.empty_cache()
         line["batches"] = [quick_batch(dev, b, L=L) for b in (8, 64) if b != B]
-        line["extra_configs"] = [quick_batch(dev, 64, mixed=True, L=L)]
+        line["extra_configs"] = [quick_batch(dev, 64, mixed=True, L=L), stream_line(dev, 8, 50, L=L)]
     if not args.no_cpu_baseline and world == 1:
         try:
             v, ms, sample, cores, parts = reference_measure(1, 0)

@@ -184,11 +184,12 @@ typedef struct {
   float norm_eps, rope_base, mag_clip;
   int rope_time_axis;                   /* 1: rotary over frames; 0: upstream quirk (no-op, skipped) */
   int max_batch, max_frames;
-  int precision;                        /* GEMM arithmetic on the tensor cores (fp32 storage, fp32 accumulate):
-                                           0 = TF32, and 3xTF32 (hi/lo split, ~fp32 products) for the ISTFT head and the
-                                               inverse-DFT GEMMs, whose outputs go through exp / sin / cos   [default]
-                                           1 = TF32 everywhere (fastest)
-                                           2 = 3xTF32 everywhere (fp32-grade; ~2.5x the codec time) */
+  int precision;                        /* arithmetic of the tensor-core GEMMs (fp32 storage, fp32 accumulate):
+                                           0 = TF32, with 3xTF32 (hi/lo operand split, fp32-grade products) for the ISTFT
+                                               head and the inverse-DFT GEMMs only ("mixed")
+                                           1 = TF32 everywhere (fastest; 3.4e-4 abs RMS on speech-level weights)
+                                           2 = 3xTF32 everywhere (fp32-grade; what the Python host passes by default:
+                                               the only mode within 1e-3 RMS of the fp32 path on adversarial heads) */
 } nt_codec_config;
 
 /* All f32, device.  Conv weights are pre-flattened tap-major: [C_out, k*C_in] with

@@ -206,6 +206,13 @@ class NeuTTS:
         c = ids.long() - base
         return c[(c >= 0) & (c < n_codes)]
 
+    def _ids_to_codes_masked(self, ids: torch.Tensor):
+        """Tensor form of ``_ids_to_codes`` for the device-side code history: (codes, keep mask), same shape as ids."""
+        shape = getattr(self.codec, "shape", None)
+        n_codes = getattr(shape, "fsq_levels", 4) ** getattr(shape, "fsq_dims", 8)
+        c = ids.long() - self.speech_base
+        return c, (c >= 0) & (c < n_codes)
+
     def _infer_torch(self, prompt_ids: list) -> str:
         """String protocol of the reference seam (``neutts/neutts.py:334-352``)."""
         out = self._generate_ids([prompt_ids])[0]
@@ -326,9 +333,6 @@ class NeuTTS:
         limit = max(limits)
         sp = lm.sampling(eos, 50, limit, 50, 1.0, seed) if min(limits) == limit else lm.sampling(eos, 50, limit, 50, 1.0, seed, limits=limits)
         dev = lm.out_tokens.device
-        base = self.speech_base
-        shape = getattr(self.codec, "shape", None)
-        n_codes = getattr(shape, "fsq_levels", 4) ** getattr(shape, "fsq_dims", 8)
         cap = max(len(r) for r in refs) + limit
         hist = torch.zeros(B, cap + 1, dtype=torch.long, device=dev)          # column `cap` is a scratch slot for masked writes
         for b, r in enumerate(refs):
@@ -345,9 +349,9 @@ class NeuTTS:
             if hi <= lo:
                 return
             ngen = lm.n_generated[:B].long()
-            seg = lm.out_tokens[:B, lo:hi].long() - base
+            seg, ok = self._ids_to_codes_masked(lm.out_tokens[:B, lo:hi].long())
             cols = torch.arange(lo, hi, device=dev)[None, :]
-            valid = (cols >= absorbed[:, None]) & (cols < ngen[:, None]) & (seg >= 0) & (seg < n_codes)
+            valid = (cols >= absorbed[:, None]) & (cols < ngen[:, None]) & ok
             pos = hlen[:, None] + torch.cumsum(valid, 1) - 1
             hist.scatter_(1, torch.where(valid, pos, torch.full_like(pos, cap)), seg)
             hlen.add_(valid.sum(1))

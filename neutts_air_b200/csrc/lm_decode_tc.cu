@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
   auto wait_go = [&](int step) -> bool {  // stream / MMA warps: released one step at a time (early-exit safety)
     uint32_t spins = 0;
     int go;
-    while ((go = *reinterpret_cast<volatile int*>(&ms->go)) >= 0 && go <= step) {
+    while ((go = atomicAdd(&ms->go, 0)) >= 0 && go <= step) {   // shared-memory atomics: a flag, not a data race
       __nanosleep(64);
       if (++spins > (1u << 25)) {
         printf("neutts_b200: decode_tc step gate timed out (block %d, warp %d)\n", blockIdx.x, warp);
@@ -1399,10 +1399,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       bool all_done = true;
       for (int b = 0; b < B; ++b) all_done = all_done && (__ldcg(P.samp.done + b) != 0);
       if (all_done || step + 1 == P.n_steps) break;
-      if (tid == 0) *reinterpret_cast<volatile int*>(&ms->go) = step + 2;
+      if (tid == 0) atomicExch(&ms->go, step + 2);
     }
     csync();
-    if (tid == 0) *reinterpret_cast<volatile int*>(&ms->go) = -1;
+    if (tid == 0) atomicExch(&ms->go, -1);
   }
   tc_fence_before();
   __syncthreads();

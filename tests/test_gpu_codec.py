@@ -72,7 +72,7 @@ def test_codec_edge_shapes(cuda):
         dec.decode_code(torch.zeros(1, 4, dtype=torch.long))
 
 
-@pytest.mark.parametrize("precision,bar", [("tf32", None), ("default", None), ("3xtf32", 1e-3)])
+@pytest.mark.parametrize("precision,bar", [("tf32", None), ("mixed", None), ("3xtf32", 1e-3)])
 def test_codec_full_size_adversarial_head_statistics(cuda, precision, bar):
     """the 1e-3 bar was only shown on synthetic weights whose head the builder scaled to speech
     level.  Here the ISTFT head is pushed to its limits: log-magnitudes up to the ``clip(max=1e2)`` edge over a band
@@ -111,7 +111,7 @@ def test_codec_full_size_adversarial_head_statistics(cuda, precision, bar):
         assert err / level * 0.1 < bar, (err, level)
 
 
-@pytest.mark.parametrize("precision", ["tf32", "default", "3xtf32"])
+@pytest.mark.parametrize("precision", ["tf32", "mixed", "3xtf32"])
 def test_codec_precision_modes_full_size(cuda, precision):
     """The standard full-size workload (speech-level synthetic weights) in every arithmetic mode: all meet 1e-3."""
     cfg = CO.CodecConfig()

