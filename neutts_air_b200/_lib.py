@@ -6,6 +6,7 @@ raised to the caller (``NT_ERR_INVALID`` -> ValueError, everything else -> Runti
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -101,11 +102,14 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    path = LIB_PATH
+    if os.environ.get("NT_LIB_PATH"):      # A/B measurements against an older build of the library (profiles/ab/)
+        path = Path(os.environ["NT_LIB_PATH"])
+    if not path.exists():
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m neutts_air_b200.build` "
+            f"{path} is missing: build it with `python -m neutts_air_b200.build` "
             "(nvcc, sm_100a). neutts_air_b200 has no CPU or PyTorch fallback.")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     L.nt_last_error.restype = C.c_char_p
     L.nt_abi_version.restype = C.c_int
     L.nt_launch_count.restype = C.c_uint64

@@ -28,6 +28,10 @@ NT_DEVINL int lane_id() { return threadIdx.x & 31; }
 // (tcgen05.mma / commit, TMA) must sit under THIS predicate inside warp-uniform control flow: behind a plain
 // `if (lane == 0)` the compiler cannot prove that a single thread is active and wraps every such instruction in an
 // ELECT / BRA.U.ANY loop with R2UR moves -- measured ~160 cycles per tcgen05.mma issue instead of back-to-back issue.
+// Call it AT the use site, after any data-dependent wait loop: elect.sync (full mask) is also the reconvergence point,
+// and the compiler emits the guarded UTMALDG / UTCHMMA unpredicated (only the operand moves carry the predicate), so
+// a diverged lane group without the leader would execute it with stale uniform registers (memcheck: out-of-range
+// shared address; found with a cached `leader` flag behind an mbarrier spin).
 NT_DEVINL bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));

@@ -108,13 +108,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // elect_one() in common.cuh: behind `if (lane == 0)` every UTCHMMA costs ~160 cycles of issue overhead).
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    const bool leader = elect_one();
     for (int kb = kb_lo; kb < kb_hi; ++kb) {
       const int s = (kb - kb_lo) % STAGES;
       const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
       const bool b_in_flight = (kb - kb_lo) < early;
       if (!b_in_flight) mbar_wait(&empty_bar[s], ph ^ 1);
-      if (leader) {
+      if (elect_one()) {   // re-elected after every wait: elect.sync is also where the lanes reconverge
         if (!b_in_flight) mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         uint8_t* sa = tiles + s * Cfg::STAGE_BYTES;
         uint8_t* sb = sa + Cfg::A_BYTES;
@@ -126,7 +125,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    const bool leader = elect_one();
     constexpr uint32_t idesc = umma_idesc(kFmt, 128, BN);
     const uint32_t tiles_addr = smem_u32(tiles);
     for (int kb = kb_lo; kb < kb_hi; ++kb) {
@@ -134,7 +132,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t ph = ((kb - kb_lo) / STAGES) & 1;
       mbar_wait(&full_bar[s], ph);
       tc_fence_after();
-      if (leader) {
+      if (elect_one()) {   // same lane every time (all 32 present): tcgen05.commit tracks the issuing thread's MMAs
         const uint32_t sa = tiles_addr + static_cast<uint32_t>(s) * Cfg::STAGE_BYTES;
         const uint32_t sb = sa + Cfg::A_BYTES;
         const uint64_t adesc = umma_desc_sw128(sa);
@@ -150,7 +148,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
       }
     }
-    if (leader) umma_commit(acc_bar);  // accumulator complete
+    if (elect_one()) umma_commit(acc_bar);  // accumulator complete
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int q = warp - 4;  // TMEM lane quarter (== warp % 4)

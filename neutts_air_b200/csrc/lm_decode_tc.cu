@@ -156,7 +156,8 @@ struct TcMisc {
   uint64_t acc_empty[2];
   uint64_t att_bar[kAttWarpsMax];
   uint32_t tmem_slot;
-  int go;                 // steps released to the stream / MMA warps so far, -1 = stop
+  uint64_t go_bar;        // step gate of the stream / MMA warps: one completion per released decode step
+  int stop;               // set before the last completion: leave instead of running the step
   int pos[kTcMaxBatch];   // this step's seq_lens snapshot
   int apage[32];          // physical pages of this CTA's attention split (this step)
   int mask_eos[kTcMaxBatch];
@@ -213,8 +214,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       mbar_init(&ms->acc_empty[i], 4);
     }
     for (int i = 0; i < kAttWarpsMax; ++i) mbar_init(&ms->att_bar[i], 1);
+    mbar_init(&ms->go_bar, 1);
     fence_barrier_init();
-    ms->go = 1;
+    ms->stop = 0;
+    mbar_arrive(&ms->go_bar);   // step 0 is released from the start
   }
   for (int i = tid; i < static_cast<int>(sizeof(TcPlan) / 4); i += kTcThreads)
     reinterpret_cast<int*>(&ms->plan)[i] = reinterpret_cast<const int*>(P.plan + blockIdx.x)[i];
@@ -233,29 +236,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
   __syncthreads();
   const int n_head_tiles = plan.head_t1 - plan.head_t0;
 
-  auto wait_go = [&](int step) -> bool {  // stream / MMA warps: released one step at a time (early-exit safety)
-    uint32_t spins = 0;
-    int go;
-    while ((go = atomicAdd(&ms->go, 0)) >= 0 && go <= step) {   // shared-memory atomics: a flag, not a data race
-      __nanosleep(64);
-      if (++spins > (1u << 25)) {
-        printf("neutts_b200: decode_tc step gate timed out (block %d, warp %d)\n", blockIdx.x, warp);
-        __trap();
-      }
-    }
-    return go >= 0;
+  // stream / MMA warps (whole warp): released one decode step at a time, so that an early exit (every sequence done)
+  // never leaves bulk copies in flight.  An mbarrier phase per step; `stop` is written before the releasing arrive.
+  auto wait_go = [&](int step) -> bool {
+    mbar_wait(&ms->go_bar, static_cast<uint32_t>(step) & 1u);
+    return *reinterpret_cast<volatile int*>(&ms->stop) == 0;
   };
-
   if (warp == 8) {
     // ================================================================== weight stream
-    // The whole warp walks the plan (warp-uniform control flow); one elected lane issues the copies.
-    const bool leader = elect_one();
+    // The whole warp walks the plan (warp-uniform control flow); one elected lane issues the copies.  elect.sync is
+    // re-executed at every use: it is also the point where the lanes RECONVERGE after a data-dependent wait loop --
+    // the compiler emits the TMA / MMA instruction itself unpredicated (only its operand moves are predicated), so a
+    // lane group that reached it without the leader would issue it with stale operands.
     int slot = 0;
     uint32_t par = 0;       // parity of the slot's NEXT completion of empty_bar that we must have seen
     bool wrapped = false;   // ring used at least once
     auto push = [&](const CUtensorMap* m, int kcol, int row) {
       if (wrapped) mbar_wait(&ms->empty_bar[slot], par ^ 1);
-      if (leader) {
+      if (elect_one()) {
         mbar_arrive_expect_tx(&ms->full_bar[slot], 16384);
         tma_load_2d(ring + static_cast<size_t>(slot) * 16384, m, kcol, row, &ms->full_bar[slot]);
       }
@@ -280,8 +278,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
   } else if (warp == 9) {
     // ================================================================== MMA issuer
     // Warp-uniform control flow, tcgen05.mma / commit under the elect.sync predicate: this is what lets the compiler
-    // keep descriptors in uniform registers and issue the MMAs back to back (see elect_one() in common.cuh).
-    const bool leader = elect_one();
+    // keep descriptors in uniform registers and issue the MMAs back to back (see elect_one() in common.cuh); elect.sync
+    // after every wait (reconvergence, see the stream warp).  With all 32 lanes present it names the same lane every
+    // time, which tcgen05.commit needs (it tracks the MMAs of the issuing thread).
     constexpr uint32_t idesc = umma_idesc(1, 128, NT);
     int slot = 0;
     uint32_t par = 0;
@@ -297,7 +296,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&ms->full_bar[slot], par);
         tc_fence_after();
-        if (leader) {
+        if (elect_one()) {
           const uint64_t adesc = umma_desc_sw128(ring_addr + static_cast<uint32_t>(slot) * 16384u);
           const uint64_t bdesc = umma_desc_sw128(bop_addr + static_cast<uint32_t>(chunk0 + kb) * CHUNK);
 #pragma unroll
@@ -307,7 +306,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         }
         if (++slot == NS) slot = 0, par ^= 1;
       }
-      if (leader) umma_commit(&ms->acc_full[buf]);
+      if (elect_one()) umma_commit(&ms->acc_full[buf]);
       ++acc_n;
     };
     const int gu_split = uniform(plan.gu_split);
@@ -396,14 +395,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       const int n = uniform(plan.n[ph]);
       if (n == 0) return;
       const int nch = uniform(ms->nchunks[ph]);
-      const bool leader = elect_one();
-      if (leader) {
+      if (elect_one()) {   // no wait inside: one election covers the whole batch of copies
         fence_proxy_async_all();
         mbar_arrive_expect_tx(&ms->bop_bar, static_cast<uint32_t>(nch) * CHUNK);
-      }
-      for (int c = 0; c < nch; ++c) {
-        const int kb = uniform(ms->ckb[ph][c]);
-        if (leader) tma_load_2d(uni + c * CHUNK, m, kb * 64, 0, &ms->bop_bar);
+        for (int c = 0; c < nch; ++c) tma_load_2d(uni + c * CHUNK, m, ms->ckb[ph][c] * 64, 0, &ms->bop_bar);
       }
     };
     auto load_bop_full = [&](const CUtensorMap* m, bool need) {  // all KBH chunks of the hidden-sized K
@@ -1399,10 +1394,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       bool all_done = true;
       for (int b = 0; b < B; ++b) all_done = all_done && (__ldcg(P.samp.done + b) != 0);
       if (all_done || step + 1 == P.n_steps) break;
-      if (tid == 0) atomicExch(&ms->go, step + 2);
+      if (tid == 0) mbar_arrive(&ms->go_bar);   // releases step + 1
     }
     csync();
-    if (tid == 0) atomicExch(&ms->go, -1);
+    if (tid == 0) {   // wake a warp that waits for a step that will not run
+      *reinterpret_cast<volatile int*>(&ms->stop) = 1;
+      mbar_arrive(&ms->go_bar);
+    }
   }
   tc_fence_before();
   __syncthreads();
