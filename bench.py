@@ -7,8 +7,13 @@
 One "step" = one pass of the hot path over one batch of utterances per GPU: prefill(500) ->
 250 decode steps (EOS masked until 250, top-k 50 / T=1 sampling on device) -> NeuCodec decode
 to 5.0 s of 24 kHz PCM.  Metric (BASELINE.json): audio-seconds per wall-second, whole job.
-Prints ONE JSON line on rank 0.  Synthetic data, seeded random weights at the inferred
-NeuTTS-Air / NeuCodec shapes (no checkpoints exist offline) — see DESIGN.md §measurement.
+N = 1: configs[1] (batch 1) + extra lines for batch 8 / 64 (`batches`), configs[2] (mixed-length
+batch 64) and configs[4] (Nano-shaped LM, batch-8 streaming, codec every 50 tokens) under
+`extra_configs`.  N > 1: configs[3], global batch 64 sharded 64 / N per GPU, waveform all-gather.
+`value`: inputs resident in HBM, CUDA events.  `e2e`: the public class (neutts.NeuTTS) with host
+buffers.  `roofline`: the decode kernel that dominates the timed region (bytes per launch / event
+time).  Prints ONE JSON line on rank 0.  Synthetic data, seeded random weights at the inferred
+NeuTTS-Air / NeuCodec shapes (no checkpoints exist offline) -- see DESIGN.md section 5.
 """
 from __future__ import annotations
 
@@ -412,7 +417,18 @@ def main_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        td.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at the first collective; the contract is ONE JSON line there
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            td.init_process_group("nccl", device_id=dev)
+            td.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(keep, 1)
+            os.close(keep)
     L = _lib.lib()
     # N = 1: configs[1] (batch 1, the configuration the metric is quoted on).  N > 1: configs[3], global batch 64
     # sharded 64 / N utterances per GPU (strong scaling: the job is fixed, the GPUs split it).
