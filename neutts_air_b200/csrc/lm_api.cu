@@ -111,7 +111,6 @@ struct nt_lm {
   float *tc_tmax = nullptr;
   float2 *tc_pq2 = nullptr, *tc_po2 = nullptr, *tc_pd2 = nullptr, *tc_ao2 = nullptr, *tc_aml2 = nullptr, *tc_act2 = nullptr, *tc_pg2 = nullptr,
          *tc_h2 = nullptr;
-  int* tc_flags = nullptr;
   size_t tc_pair_bytes = 0;           // extent of the stamped buffers (contiguous, starting at tc_pq2)
   int tc_stamp = 0, tc_hstamp = 0;    // stamps handed out so far (see TcParams::stamp_base)
 };
@@ -169,7 +168,6 @@ static size_t lm_carve(const nt_lm_config& c, void* ws, size_t bytes, F&& assign
     (L)->tc_aml2 = a.take<float2>(size_t((L)->tc_rows) * c.n_heads * max_splits * 2);          \
     (L)->tc_act2 = a.take<float2>(size_t(4) * I);                                              \
     (L)->tc_pg2 = a.take<float2>(size_t(kTcMaxGuSlices) * 4 * 2 * I);                          \
-    (L)->tc_flags = a.take<int>(64 + 4096);                                                    \
     (L)->tc_h2 = a.take<float2>(size_t(2) * 4 * H);                                            \
     (L)->tc_pair_bytes = size_t(reinterpret_cast<uint8_t*>((L)->tc_h2 + size_t(2) * 4 * H) - reinterpret_cast<uint8_t*>((L)->tc_pq2)); \
   }
@@ -594,7 +592,7 @@ extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps
     const int pi = (lm->tc_flat_ok && tc_fold_in_cta(B, c.hidden)) ? 1 : 0;
     const TcPlanInfo& info = lm->tc_info[pi];
     P.plan = lm->tc_plan + 256 * pi;
-    P.pg2 = lm->tc_pg2, P.gu_nsl = lm->tc_gu_nsl, P.flags = lm->tc_flags;
+    P.pg2 = lm->tc_pg2, P.gu_nsl = lm->tc_gu_nsl;
     P.ln1 = lm->ptr_tab, P.bqkv = lm->ptr_tab + c.n_layers, P.ln2 = lm->ptr_tab + 2 * c.n_layers;
     P.final_norm = lm->final_norm, P.inv_freq = lm->inv_freq;
     P.h = lm->h, P.xa = lm->tc_xa, P.act = lm->tc_act;

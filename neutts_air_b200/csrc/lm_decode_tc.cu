@@ -38,12 +38,6 @@
 namespace nt {
 
 // ------------------------------------------------------------------------------------------ small device helpers
-NT_DEVINL int tc_ld_acquire_i(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-NT_DEVINL void tc_st_release_i(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 NT_DEVINL unsigned tc_ld_acquire(const unsigned* p) {
   unsigned v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -422,29 +416,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       if (tid == 0) mbar_arrive(&ms->bop_bar);
     };
 
-    // ---- batch > 1 hand-off of a TMA-fed B operand WITHOUT a grid barrier: warp 0 waits for the flags of what it is
-    //      about to fetch (all token rows of xa, or the SwiGLU tiles of its k-blocks), then issues the copies.
-    //      Safe against overwrites by construction: the next writer of xa / act depends, through the partial sums it
-    //      folds, on every consumer of the previous contents having finished its MMAs.
-    auto wait_load = [&](const CUtensorMap* m, bool full, int lph, bool need, bool tiles, int stamp) {
-      csync();   // this CTA is through with the previous contents of the B chunks
-      if (warp == 0) {
-        const bool mine = full ? need : uniform(plan.n[lph]) > 0;
-        if (mine) {
-          const int n = tiles ? uniform(ms->nchunks[lph]) : B;
-          for (int i = lane; i < n; i += 32) {
-            const int* f = tiles ? P.flags + 64 + ms->ckb[lph][i] : P.flags + i;
-            uint32_t spins = 0;
-            while (tc_ld_acquire_i(f) != stamp) tc_spin_check(spins, tiles ? "SwiGLU tiles" : "normalised rows");
-          }
-          __syncwarp();
-          if (full) load_bop_full(m, true);
-          else load_bop_split(m, lph);
-        }
-      }
-      csync();
-    };
-
     // ---- accumulator of the next item -> registers (epilogue warps 0..3; lane = weight row of the tile)
     auto acc_take = [&](float (&v)[NT]) {
       const uint32_t buf = acc_n & 1;
@@ -506,12 +477,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
     };
 
     // ---- batch > 4: fold + RMSNorm of ONE token row by its owner CTA -> residual stream (fp32) + normalised bf16 rows
-    //      Returns the stamp the row is published under (flags[b]): consumers wait for it instead of a grid barrier.
-    auto fold_phase = [&](const float2* parts, int nparts, int pstamp, int rows, const float* norm_w) -> int {
-      const int xstamp = P.hstamp_base + 1 + fold_no;
-      ++fold_no;
+    auto fold_phase = [&](const float2* parts, int nparts, int pstamp, int rows, const float* norm_w) {
       const int b = blockIdx.x;
-      if (b >= B) return xstamp;
+      if (b >= B) return;
       float* hb = P.h + static_cast<long long>(b) * H;
       float ss = 0.f;
       for (int i4 = tid * 4; i4 < H; i4 += 4 * kConsumerThreads) {
@@ -546,10 +514,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
               make_uint2(pack_bf16x2(xn[0], xn[1]), pack_bf16x2(xn[2], xn[3]));
         }
       }
-      __threadfence();   // every thread's part of the row -> gpu scope, then one release store names it complete
-      csync();
-      if (tid == 0) tc_st_release_i(P.flags + b, xstamp);
-      return xstamp;
     };
 
     // ---- batch <= 4: fold ALL rows in this CTA (residual pairs + slices, slice order), normalise, stage the B chunks
@@ -983,11 +947,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
             }
           }
         }
-        if constexpr (!FOLD) {   // publish the tile: the down_proj CTAs that fetch these activations wait for its flag
-          __threadfence();
-          bar_epi();
-          if (tid == 0) tc_st_release_i(P.flags + 64 + it.tile, stamp);
-        }
       }
     };
 
@@ -1378,18 +1337,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
         // ---------------- batch > 4: token-owner fold phases feed the consumers by TMA (3 barriers per layer).
         // Segments of a layer, each entered through a grid barrier whose post step fetches the B operand:
         //   0: qkv epilogue, attention, merge + o_proj, fold -> 1: gate/up + SwiGLU -> 2: down_proj, fold
-        int xs = fold_phase(nullptr, 0, 0, H, L > 0 ? P.ln1[0] : P.final_norm);
+        fold_phase(nullptr, 0, 0, H, L > 0 ? P.ln1[0] : P.final_norm);
         for (int q = 0;; ++q) {
           const int l = q / 3, seg = q - 3 * l;
           const int st = stamp_of(step, l);
           const bool head = l == L;
           {
             const bool full = head || seg == 1;
-            const CUtensorMap* m = seg == 2 && !head ? amap : xmap;
+            const CUtensorMap* m = seg == 2 ? amap : xmap;
             const int lph = seg == 0 ? kPhQ : kPhD;
             const bool need = head ? n_head_tiles > 0 : plan.n[kPhG] > 0;
-            const bool tiles = seg == 2 && !head;
-            wait_load(m, full, lph, need, tiles, tiles ? st : xs);
+            grid_sync([&] {
+              if (full) load_bop_full(m, need);
+              else load_bop_split(m, lph);
+            });
           }
           if (head) break;
           prof.fine = prof.buf != nullptr && l == 2;
@@ -1410,8 +1371,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
             if (tid == 0) prof.mark(100 + ph + (ph > 0 ? 1 : 0));   // 100 qkv, 102 o_proj, 103 gate/up, 104 down
           }
           const bool last = l + 1 == L;
-          if (seg == 0) xs = fold_phase(P.po2, P.so, st, H, P.ln2[l]);
-          else xs = fold_phase(P.pd2, P.sd, st, H, last ? P.final_norm : P.ln1[l + 1]);
+          if (seg == 0) fold_phase(P.po2, P.so, st, H, P.ln2[l]);
+          else fold_phase(P.pd2, P.sd, st, H, last ? P.final_norm : P.ln1[l + 1]);
           if (tid == 0) prof.mark(seg == 0 ? 105 : 106);
         }
       }

@@ -64,8 +64,6 @@ struct TcParams {
   float2* pg2;                    // batch <= 4, flat plan: gate/up partial sums [slice][B][2 * inter]
   const unsigned char* gu_nsl;    // flat plan: K slices of every gate/up tile (device, [tiles])
   float2* h2;                     // batch <= 4: residual stream, ping-pong [2][B][hidden]
-  int* flags;                     // batch > 1: [0, 64) stamp of the last published xa row of every token, [64, 64 + tiles) stamp of
-                                  //   the last published SwiGLU tile: consumers wait on the rows / tiles they fetch (no grid barrier)
   int stamp_base, hstamp_base;    // stamps of this launch lie above these (host counters)
   int max_splits, split_cap;
   KVLayout kv;
