@@ -74,13 +74,16 @@ NT_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// out of line on purpose: the report is cold code, inlined it would sit (printf argument set-up and all) in the
+// instruction stream of every wait loop of kernels that already fight for the instruction cache
+__device__ __noinline__ inline void nt_timeout(const char* what) {
+  printf("neutts_b200: timed out waiting for %s (block %d,%d thread %d)\n", what, blockIdx.x, blockIdx.y, threadIdx.x);
+  __trap();
+}
 NT_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > NT_SPIN_LIMIT) {
-      printf("neutts_b200: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
+    if (++spins > NT_SPIN_LIMIT) nt_timeout("an mbarrier");
   }
 }
 

@@ -95,10 +95,7 @@ NT_DEVINL __nv_bfloat16* chunk_elem(uint8_t* chunk, int n, int k) {
 
 
 NT_DEVINL void tc_spin_check(uint32_t& spins, const char* what) {
-  if (++spins > (1u << 22)) {
-    printf("neutts_b200: decode_tc poll timed out waiting for %s (block %d thread %d)\n", what, blockIdx.x, threadIdx.x);
-    __trap();
-  }
+  if (++spins > (1u << 22)) nt_timeout(what);
 }
 
 // 4 consecutive elements of row b: residual pairs (or nothing) + the split-K slices in slice order; polls the stamps
@@ -374,10 +371,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
           atomicAdd(P.gbar, 1u);
           uint32_t spins = 0;
           while (tc_ld_acquire(P.gbar) < target) {
-            if (++spins > (1u << 24)) {
-              printf("neutts_b200: decode_tc grid barrier timed out (block %d, target %u, seen %u)\n", blockIdx.x, target, *P.gbar);
-              __trap();
-            }
+            if (++spins > (1u << 24)) nt_timeout("the grid barrier");
           }
           prof.mark(200);
         }
