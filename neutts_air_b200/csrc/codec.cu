@@ -271,9 +271,10 @@ __global__ void split_tf32_kernel(const float* __restrict__ x, float* __restrict
 
 using namespace nt;
 
-struct SplitW {   // hi / lo halves of one weight matrix (workspace), null when the matrix runs in plain TF32
-  float* hi = nullptr;
+struct SplitW {   // hi / lo halves of one weight matrix (workspace: lo directly below hi, `rows` rows further down);
+  float* hi = nullptr;   // null when the matrix runs in plain TF32
   float* lo = nullptr;
+  int rows = 0;
 };
 
 struct nt_codec {
@@ -285,7 +286,7 @@ struct nt_codec {
   // 3xTF32 (cfg.precision != 1): split weights, split-activation scratch, partial-sum scratch
   SplitW s_head, s_idft, s_embed;
   std::vector<SplitW> s_rn[2], s_blk[4];   // resnet conv1 / conv2; wqkv, wproj, fc1, fc2
-  float *a_hi = nullptr, *a_lo = nullptr, *acc = nullptr;
+  float* a_split = nullptr;   // hi half, then the lo half a_rows rows further down (placed per GEMM)
 };
 
 static int codec_check(const nt_codec_config* c) {
@@ -319,28 +320,30 @@ static size_t codec_carve(const nt_codec_config& c, void* ws, size_t bytes, nt_c
   k->inv_freq = a.take<float>(64);
   if (c.precision != 1) {
     const size_t C = c.hidden, nb2 = size_t(c.n_fft) + 2;
-    auto takew = [&](SplitW& w, size_t n) { w.hi = a.take<float>(n), w.lo = a.take<float>(n); };
-    takew(k->s_head, nb2 * C);
-    takew(k->s_idft, size_t(c.n_fft) * kpad);
+    auto takew = [&](SplitW& w, size_t rows_, size_t ld) {   // one block: hi rows, then lo rows
+      w.hi = a.take<float>(2 * rows_ * ld);
+      w.lo = w.hi + rows_ * ld;
+      w.rows = int(rows_);
+    };
+    takew(k->s_head, nb2, C);
+    takew(k->s_idft, size_t(c.n_fft), kpad);
     size_t widest = kpad > c.n_fft ? kpad : c.n_fft;
     if (c.precision == 2) {
-      takew(k->s_embed, C * c.embed_kernel * C);
+      takew(k->s_embed, C, c.embed_kernel * C);
       for (int i = 0; i < 2; ++i) {
         k->s_rn[i].assign(4, SplitW());
-        for (int j = 0; j < 4; ++j) takew(k->s_rn[i][j], C * 3 * C);
+        for (int j = 0; j < 4; ++j) takew(k->s_rn[i][j], C, 3 * C);
       }
-      const size_t bn[4] = {3 * C * C, C * C, size_t(c.mlp_hidden) * C, C * size_t(c.mlp_hidden)};
+      const size_t br[4] = {3 * C, C, size_t(c.mlp_hidden), C}, bl[4] = {C, C, C, size_t(c.mlp_hidden)};
       for (int i = 0; i < 4; ++i) {
         k->s_blk[i].assign(c.depth, SplitW());
-        for (int j = 0; j < c.depth; ++j) takew(k->s_blk[i][j], bn[i]);
+        for (int j = 0; j < c.depth; ++j) takew(k->s_blk[i][j], br[i], bl[i]);
       }
       if (size_t(c.mlp_hidden) > widest) widest = c.mlp_hidden;
       if (3 * C > widest) widest = 3 * C;
     }
     if (C > widest) widest = C;
-    k->a_hi = a.take<float>(rows * widest);
-    k->a_lo = a.take<float>(rows * widest);
-    k->acc = a.take<float>(rows * widest);
+    k->a_split = a.take<float>(2 * rows * widest);
   }
   return a.off;
 }
@@ -420,8 +423,8 @@ struct CodecRun {
 
   // masked GEMM on the padded layout: out rows r+3 for r with (r % Tp) < N.
   // A points at the first row the tap window of output row 0 touches.
-  // sw (optional): the weight's hi / lo halves -> 3xTF32: acc = residual + A_lo.W_hi; acc += A_hi.W_lo;
-  // out = act(bias + acc + A_hi.W_hi) (small terms first; bias / activation only in the last pass).
+  // sw (optional): the weight's hi / lo halves -> 3xTF32 in one pass of the GEMM kernel (A_lo.W_hi + A_hi.W_lo +
+  // A_hi.W_hi into one TMEM accumulator); the activations are split into a hi / lo pair of buffers first.
   int gemm(const float* A, int K, int lda, const float* W, const float* bias, const float* residual, nt_act act, float* out,
            int ldc, int Nout, bool masked, const SplitW* sw = nullptr, int ldw = 0) {
     nt_gemm_args a;
@@ -432,18 +435,14 @@ struct CodecRun {
     a.bias = bias, a.residual = residual, a.ldr = ldc, a.act = act, a.out_f32 = out, a.ldc = ldc;
     if (masked) a.valid_period = Tp, a.valid_len = N;
     if (!sw || !sw->hi) return gemm_dispatch(a, s, nullptr, true);
-    const long long a_elems = static_cast<long long>(a.M + (K + lda - 1) / lda - 1) * lda;   // rows the tap window touches
-    const int lda_acc = (Nout + 3) & ~3;
-    int rc = launch_kernel(split_tf32_kernel, dim3(296), dim3(256), 0, s, true, A, k->a_hi, k->a_lo, a_elems);
+    const int a_rows = a.M + (K + lda - 1) / lda - 1;                      // rows the tap window touches
+    const long long a_elems = static_cast<long long>(a_rows) * lda;
+    float* a_hi = k->a_split;
+    int rc = launch_kernel(split_tf32_kernel, dim3(296), dim3(256), 0, s, true, A, a_hi, a_hi + a_elems, a_elems);
     if (rc) return rc;
-    nt_gemm_args p = a;
-    p.bias = nullptr, p.act = NT_ACT_NONE, p.out_f32 = k->acc, p.ldc = lda_acc;
-    p.A = k->a_lo, p.W = sw->hi;                                     // pass 1: acc = residual + A_lo.W_hi
-    if ((rc = gemm_dispatch(p, s, nullptr, true))) return rc;
-    p.A = k->a_hi, p.W = sw->lo, p.residual = k->acc, p.ldr = lda_acc;  // pass 2: acc += A_hi.W_lo
-    if ((rc = gemm_dispatch(p, s, nullptr, true))) return rc;
-    a.A = k->a_hi, a.W = sw->hi, a.residual = k->acc, a.ldr = lda_acc;  // pass 3: out = act(bias + acc + A_hi.W_hi)
-    return gemm_dispatch(a, s, nullptr, true);
+    a.A = a_hi, a.W = sw->hi;
+    const Split3 s3{a_rows, sw->rows};
+    return gemm_dispatch(a, s, nullptr, true, &s3);
   }
   const SplitW* sp(const std::vector<SplitW>& v, int i) const { return v.empty() ? nullptr : &v[i]; }
   int resnet(int idx) {

@@ -35,21 +35,27 @@ struct GemmEpilogue {
 
 // kShallow: half-depth ring (<= 113 KB) so two CTAs share an SM -- used when the grid is between one and two
 // waves of single-occupancy CTAs (e.g. gate/up at batched decode: 152 tiles on 148 SMs would take two rounds).
-template <int BN, bool kShallow = false>
+// kS3 (tf32 only): 3xTF32 in ONE pass.  Both operands arrive as hi/lo halves (hi = the value rounded to TF32, lo = the
+// exact remainder), the lo half stored `*_lo_rows` rows below the hi half in the same matrix, so one tensor map per
+// operand serves both; a stage holds A_hi | A_lo | W_hi | W_lo and every k-block issues A_lo.W_hi, A_hi.W_lo, A_hi.W_hi
+// into the same TMEM accumulator: fp32-grade products on the TF32 pipe without intermediate round trips to HBM.
+template <int BN, bool kShallow = false, bool kS3 = false>
 struct GemmCfg {
   static constexpr int BM = 128;
   static constexpr int A_BYTES = BM * 128;
   static constexpr int B_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = kShallow ? (BN <= 64 ? 4 : 3) : ((BN <= 64) ? 8 : (BN == 128 ? 6 : 4));
+  static constexpr int STAGE_BYTES = (kS3 ? 2 : 1) * (A_BYTES + B_BYTES);
+  static constexpr int STAGES = kS3 ? (BN == 128 ? 3 : (BN == 64 ? 4 : 5))
+                                    : (kShallow ? (BN <= 64 ? 4 : 3) : ((BN <= 64) ? 8 : (BN == 128 ? 6 : 4)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int kFmt, int BN, bool kShallow>
+template <int kFmt, int BN, bool kShallow, bool kS3 = false>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmEpilogue ep, int M,
-               int N, int num_kb, int kb_per_tap) {
-  using Cfg = GemmCfg<BN, kShallow>;
+               int N, int num_kb, int kb_per_tap, int a_lo_rows, int w_lo_rows) {
+  using Cfg = GemmCfg<BN, kShallow, kS3>;
+  constexpr int W_OFF = (kS3 ? 2 : 1) * Cfg::A_BYTES;   // byte offset of the W tile(s) inside a stage
   constexpr int STAGES = Cfg::STAGES;
   constexpr int BK_ELEMS = (kFmt == 2) ? 32 : 64;  // 128 bytes along K
 
@@ -98,7 +104,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       for (int i = 0; i < early; ++i) {
         mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
-        tma_load_2d(tiles + i * Cfg::STAGE_BYTES + Cfg::A_BYTES, &tmB, (kb_lo + i) * BK_ELEMS, n0, &full_bar[i]);
+        tma_load_2d(tiles + i * Cfg::STAGE_BYTES + W_OFF, &tmB, (kb_lo + i) * BK_ELEMS, n0, &full_bar[i]);
+        if (kS3) tma_load_2d(tiles + i * Cfg::STAGE_BYTES + W_OFF + Cfg::B_BYTES, &tmB, (kb_lo + i) * BK_ELEMS, n0 + w_lo_rows, &full_bar[i]);
       }
     }
   }
@@ -116,11 +123,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (elect_one()) {   // re-elected after every wait: elect.sync is also where the lanes reconverge
         if (!b_in_flight) mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         uint8_t* sa = tiles + s * Cfg::STAGE_BYTES;
-        uint8_t* sb = sa + Cfg::A_BYTES;
+        uint8_t* sb = sa + W_OFF;
         const int tap = kb / kb_per_tap;
         const int acol = (kb - tap * kb_per_tap) * BK_ELEMS;
         tma_load_2d(sa, &tmA, acol, m0 + tap, &full_bar[s]);
-        if (!b_in_flight) tma_load_2d(sb, &tmB, kb * BK_ELEMS, n0, &full_bar[s]);
+        if (kS3) tma_load_2d(sa + Cfg::A_BYTES, &tmA, acol, m0 + tap + a_lo_rows, &full_bar[s]);
+        if (!b_in_flight) {
+          tma_load_2d(sb, &tmB, kb * BK_ELEMS, n0, &full_bar[s]);
+          if (kS3) tma_load_2d(sb + Cfg::B_BYTES, &tmB, kb * BK_ELEMS, n0 + w_lo_rows, &full_bar[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -134,16 +145,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       if (elect_one()) {   // same lane every time (all 32 present): tcgen05.commit tracks the issuing thread's MMAs
         const uint32_t sa = tiles_addr + static_cast<uint32_t>(s) * Cfg::STAGE_BYTES;
-        const uint32_t sb = sa + Cfg::A_BYTES;
+        const uint32_t sb = sa + W_OFF;
         const uint64_t adesc = umma_desc_sw128(sa);
         const uint64_t bdesc = umma_desc_sw128(sb);
+        if (kS3) {   // small terms first: A_lo.W_hi, A_hi.W_lo, then A_hi.W_hi
+          const uint64_t alo = umma_desc_sw128(sa + Cfg::A_BYTES), blo = umma_desc_sw128(sb + Cfg::B_BYTES);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per stage
-          const uint32_t acc = (kb > kb_lo || k > 0) ? 1u : 0u;
-          if (kFmt == 2)
-            umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
-          else
-            umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+          for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, alo + 2 * k, bdesc + 2 * k, idesc, (kb > kb_lo || k > 0) ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, adesc + 2 * k, blo + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // 4 x 32 bytes of K per stage
+            const uint32_t acc = (kb > kb_lo || k > 0) ? 1u : 0u;
+            if (kFmt == 2)
+              umma_tf32(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+            else
+              umma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, acc);
+          }
         }
         umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
       }
@@ -300,20 +321,20 @@ int make_tmap(CUtensorMap* out, nt_dtype dt, const void* base, uint64_t rows, ui
   return NT_OK;
 }
 
-template <int kFmt, int BN, bool kShallow>
+template <int kFmt, int BN, bool kShallow, bool kS3 = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int num_kb,
-                       int kb_per_tap, cudaStream_t stream) {
+                       int kb_per_tap, cudaStream_t stream, int a_lo_rows = 0, int w_lo_rows = 0) {
   const int splits = ep.split_k > 1 ? ep.split_k : 1;
-  using Cfg = GemmCfg<BN, kShallow>;
+  using Cfg = GemmCfg<BN, kShallow, kS3>;
   static bool attr_set = false;
-  auto kern = gemm_tc_kernel<kFmt, BN, kShallow>;
+  auto kern = gemm_tc_kernel<kFmt, BN, kShallow, kS3>;
   if (!attr_set) {
     NT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + Cfg::BM - 1) / Cfg::BM, splits);
   return launch_kernel(kern, grid, dim3(256), Cfg::SMEM_BYTES, stream, /*pdl=*/true, ta, tb, ep, M, N, num_kb,
-                       kb_per_tap);
+                       kb_per_tap, a_lo_rows, w_lo_rows);
 }
 
 static int num_sms() {
@@ -326,7 +347,7 @@ static int num_sms() {
   return n;
 }
 
-int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, bool w_const) {
+int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, bool w_const, const Split3* s3) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error(NT_ERR_INVALID, "gemm: empty problem");
   const int esz = a.dtype == NT_BF16 ? 2 : 4;
   const int bk = 128 / esz;
@@ -358,10 +379,12 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, boo
   if (mt * ((a.N + 63) / 64) < 100) bn = 32;
   if (a.act == NT_ACT_SWIGLU && bn < 64) bn = 64;
 
+  if (s3 && (a.dtype != NT_TF32 || split)) return set_error(NT_ERR_INVALID, "gemm: 3xTF32 needs tf32 operands and no split-K");
   CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, a.dtype, a.A, a_rows, a_cols, a.lda, 128);
+  // 3xTF32: the lo halves lie a_lo_rows / w_lo_rows rows below the hi halves in the same matrices
+  int rc = make_tmap(&ta, a.dtype, a.A, s3 ? uint64_t(s3->a_lo_rows) + a_rows : a_rows, a_cols, a.lda, 128);
   if (rc) return rc;
-  rc = make_tmap(&tb, a.dtype, a.W, a.N, a.K, a.ldw, bn);
+  rc = make_tmap(&tb, a.dtype, a.W, s3 ? uint64_t(s3->w_lo_rows) + a.N : a.N, a.K, a.ldw, bn);
   if (rc) return rc;
 
   GemmEpilogue ep;
@@ -410,6 +433,11 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, boo
 #define NT_GEMM_CASE(FMT, BNV)                                                                           \
   return shallow ? launch_gemm<FMT, BNV, true>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)         \
                  : launch_gemm<FMT, BNV, false>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream)
+  if (s3) {
+    if (bn == 128) return launch_gemm<2, 128, false, true>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream, s3->a_lo_rows, s3->w_lo_rows);
+    if (bn == 64) return launch_gemm<2, 64, false, true>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream, s3->a_lo_rows, s3->w_lo_rows);
+    return launch_gemm<2, 32, false, true>(ta, tb, ep, a.M, a.N, num_kb, kb_per_tap, stream, s3->a_lo_rows, s3->w_lo_rows);
+  }
   if (a.dtype == NT_BF16) {
     if (bn == 128) NT_GEMM_CASE(1, 128);
     if (bn == 64) NT_GEMM_CASE(1, 64);

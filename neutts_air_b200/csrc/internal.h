@@ -59,7 +59,13 @@ struct SplitK {
   long long slice_stride;  // out: floats between slices
 };
 // w_const: W holds model weights that no kernel writes, so the kernel may fetch them ahead of the PDL dependency
-int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split = nullptr, bool w_const = false);
+// 3xTF32 in one pass (gemm_tc.cu): a.A / a.W point at the hi halves, the lo halves lie a_lo_rows / w_lo_rows rows
+// further down in the same matrices (same row strides)
+struct Split3 {
+  int a_lo_rows, w_lo_rows;
+};
+int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split = nullptr, bool w_const = false,
+                  const Split3* s3 = nullptr);
 
 // 2-D TMA descriptor over a row-major matrix (rows x cols elements, row stride ld elements); box = box_rows x 128
 // bytes, SWIZZLE_128B (gemm_tc.cu)

@@ -106,18 +106,18 @@ def test_lm_ragged_batch_prefill_and_decode(cuda, mega, monkeypatch):
         assert rel_err(got[b], mir) < 6e-3 and max_err(got[b], mir) < 5e-2 * float(mir.std()), (b, rel_err(got[b], mir))
 
 
-@pytest.mark.parametrize("B,mega_max", [(6, None), (18, None), (10, "16")],
-                         ids=["per-op-tcgen05-b6", "per-op-tcgen05-b18", "3-megakernel-instances"])
-def test_lm_batched_decode(cuda, B, mega_max, monkeypatch):
-    """batch > 4 decodes through the per-op chain with tcgen05 GEMMs, M = batch (bf16 GEMM inputs, split-K
-    o/down projections folded by the next RMSNorm).  NT_MEGA_MAX_BATCH=16 instead runs concurrent megakernel
-    instances of <= 4 sequences on disjoint SM subsets (fp32 activations, same arithmetic as batch 1).
-    Prefill is the tensor-core path in every case, so the bar is the pure-reference one."""
-    if mega_max:
-        monkeypatch.setenv("NT_MEGA_MAX_BATCH", mega_max)
-    cfg, w, lm = _setup(SMALL, 31, max_batch=20, max_ctx=256)
+@pytest.mark.parametrize("B,impl", [(6, None), (10, None), (18, None), (18, "tc"), (34, "tc"), (7, "perop")],
+                         ids=["persistent-b6-hilo", "persistent-b10-bf16", "chain-b18", "persistent-b18-n32", "persistent-b34-n64", "chain-b7"])
+def test_lm_batched_decode(cuda, B, impl, monkeypatch):
+    """Batched decode, every kernel variant: the persistent tcgen05 kernel with bf16 hi+lo activations (batch <= 8),
+    with plain bf16 activations on N = 16 / 32 / 64 token columns (the default up to batch 16; larger batches forced
+    with NT_DECODE_IMPL=tc), and the per-op chain (default from batch 17; forced at batch 7).  Prefill is the
+    tensor-core path in every case, so the bar is the pure-reference one."""
+    if impl:
+        monkeypatch.setenv("NT_DECODE_IMPL", impl)
+    cfg, w, lm = _setup(SMALL, 31, max_batch=36, max_ctx=256)
     g = torch.Generator().manual_seed(2)
-    lens = [20, 41, 64, 65, 9, 30, 17, 80, 33, 5, 12, 70, 3, 44, 27, 90, 61, 8][:B]
+    lens = ([20, 41, 64, 65, 9, 30, 17, 80, 33, 5, 12, 70, 3, 44, 27, 90, 61, 8] * 2)[:B]
     n_new, eos = 4, cfg.vocab_size - 1
     prompts = [torch.randint(0, cfg.vocab_size, (n,), generator=g) for n in lens]
     forced = torch.randint(0, cfg.vocab_size, (B, n_new), generator=g)
