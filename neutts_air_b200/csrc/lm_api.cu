@@ -434,7 +434,10 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
     if ((rc = gemm_dispatch(a, stream, allow_split ? &qsplit : nullptr, true))) return rc;
     const int32_t* tseq = mode == 0 ? lm->tok_seq : lm->iota;
     const int32_t* tpos = mode == 0 ? lm->tok_pos : st->seq_lens;
-    if ((rc = launch_rope_append(qsplit.used > 1 ? qsplit.ws : lm->qkv, rows, QN, tseq, tpos, c.n_heads, lm->inv_freq, lm->q, kv, l, stream,
+    // decode on the tensor-core attention kernel (batch > 4): RoPE + KV append run in that kernel's prologue
+    const bool fuse_rope = mode == 1 && B > 4 && !env_flag("NT_NO_FUSED_ROPE");
+    if (!fuse_rope &&
+        (rc = launch_rope_append(qsplit.used > 1 ? qsplit.ws : lm->qkv, rows, QN, tseq, tpos, c.n_heads, lm->inv_freq, lm->q, kv, l, stream,
                                  qsplit.used, qsplit.slice_stride)))
       return rc;
     if (mode == 0) {
@@ -444,9 +447,14 @@ static int layers_gemm(nt_lm* lm, const nt_lm_state* st, int rows, int B, int mo
       if ((rc = launch_attn_prefill(ap, B, c.n_layers, stream))) return rc;
     } else {
       AttnDecParams ad;
+      memset(&ad, 0, sizeof(ad));
       ad.q = lm->q, ad.kv = kv, ad.layer = l, ad.n_heads = c.n_heads, ad.n_rep = c.n_heads / c.n_kv_heads;
       ad.scale_log2 = scale_log2, ad.part_o = lm->part_o, ad.part_ml = lm->part_ml, ad.counters = lm->counters;
       ad.out = lm->attn, ad.out_bf16 = lm->attn_bf16, ad.max_splits = lm->max_splits;
+      if (fuse_rope) {
+        ad.qkv = qsplit.used > 1 ? qsplit.ws : lm->qkv, ad.qkv_n = QN, ad.qkv_parts = qsplit.used;
+        ad.qkv_pstride = qsplit.slice_stride, ad.inv_freq = lm->inv_freq;
+      }
       if ((rc = launch_attn_decode(ad, B, c.n_layers, stream))) return rc;
     }
     memset(&a, 0, sizeof(a));
@@ -529,6 +537,7 @@ static int decode_step(nt_lm* lm, const nt_lm_state* st, int B, const nt_samplin
       if ((rc = launch_gemv(g, B, lm->num_sms, stream))) return rc;
 
       AttnDecParams ad;
+      memset(&ad, 0, sizeof(ad));
       ad.q = lm->q, ad.kv = kv, ad.layer = l, ad.n_heads = c.n_heads, ad.n_rep = c.n_heads / c.n_kv_heads;
       ad.scale_log2 = scale_log2, ad.part_o = lm->part_o, ad.part_ml = lm->part_ml, ad.counters = lm->counters;
       ad.out = lm->attn, ad.out_bf16 = nullptr, ad.max_splits = lm->max_splits;

@@ -331,6 +331,8 @@ struct AttnMmaSmem {
   float o[8][8][64];   // per-warp unnormalised outputs [head][dim]
   float ml[8][8][2];
   uint64_t bar[8];
+  float q[8][64];      // fused prologue: this group's rotated queries, the new token's K / V row
+  float knew[64], vnew[64];
 };
 __global__ void __launch_bounds__(256) attn_decode_mma_kernel(const AttnDecParams p, const __grid_constant__ CUtensorMap kvmap) {
   extern __shared__ uint8_t attn_raw[];
@@ -344,18 +346,59 @@ __global__ void __launch_bounds__(256) attn_decode_mma_kernel(const AttnDecParam
     fence_barrier_init();
   }
   pdl_wait();
-  const int n_ctx = min(__ldcg(p.kv.seq_lens + b) + 1, p.kv.max_ctx);
+  const int pos = __ldcg(p.kv.seq_lens + b);   // position of the new token
+  const int n_ctx = min(pos + 1, p.kv.max_ctx);
   const int npages = (n_ctx + 63) >> 6;
   const int g = lane >> 2, t = lane & 3, lrow = lane & 7, lmat = lane >> 3;
+  const bool fused = p.qkv != nullptr;
+  const bool appends = fused && pos < p.kv.max_ctx;
+  if (fused) {
+    // RoPE + KV append of this (sequence, kv head) -- what rope_append_kernel did in a launch of its own: pair u of a
+    // head holds dims (i, i + 32) (rows are pair-interleaved at pack time), V is plain.  Slices summed in slice order.
+    const float* row = p.qkv + static_cast<long long>(b) * p.qkv_n;
+    const int n_kv = p.kv.n_kv_heads;
+    for (int idx = tid; idx < (n_rep + 2) * 32; idx += 256) {
+      const int which = idx < n_rep * 32 ? 0 : (idx < n_rep * 32 + 32 ? 1 : 2);
+      const int i = idx & 31;
+      const int col = (which == 0 ? (kvh * n_rep + (idx >> 5)) : (which == 1 ? p.n_heads + kvh : p.n_heads + n_kv + kvh)) * 64 + 2 * i;
+      float2 v = __ldcg(reinterpret_cast<const float2*>(row + col));
+      for (int z = 1; z < p.qkv_parts; ++z) {
+        const float2 w = __ldcg(reinterpret_cast<const float2*>(row + z * p.qkv_pstride + col));
+        v.x += w.x, v.y += w.y;
+      }
+      if (which == 2) {
+        sm->vnew[2 * i] = v.x, sm->vnew[2 * i + 1] = v.y;
+      } else {
+        float sn, cs;
+        sincosf(static_cast<float>(pos) * __ldg(p.inv_freq + i), &sn, &cs);
+        const float lo = v.x * cs - v.y * sn, hi = v.y * cs + v.x * sn;
+        if (which == 0) sm->q[idx >> 5][i] = lo, sm->q[idx >> 5][i + 32] = hi;
+        else sm->knew[i] = lo, sm->knew[i + 32] = hi;
+      }
+    }
+    __syncthreads();
+    if (appends && tid < 64) {   // the row joins the cache for the steps to come; this step patches it into the staged page
+      const int page = __ldcg(p.kv.page_table + b * p.kv.max_pages_per_seq + (pos >> 6));
+      p.kv.page_ptr(p.layer, 0, page, kvh)[(pos & 63) * 64 + tid] = __float2bfloat16(sm->knew[tid]);
+      p.kv.page_ptr(p.layer, 1, page, kvh)[(pos & 63) * 64 + tid] = __float2bfloat16(sm->vnew[tid]);
+    }
+  }
   // query fragments: row g = head g of the group (rows >= n_rep and rows 8..15 are zero)
   uint32_t qa[4][4];
   {
-    const float* qp = p.q + (static_cast<long long>(b) * p.n_heads + kvh * n_rep + min(g, n_rep - 1)) * 64;
+    const float* qp = fused ? sm->q[min(g, n_rep - 1)]
+                            : p.q + (static_cast<long long>(b) * p.n_heads + kvh * n_rep + min(g, n_rep - 1)) * 64;
     const float sc = (g < n_rep) ? p.scale_log2 : 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 a0 = __ldcg(reinterpret_cast<const float2*>(qp + 16 * j + 2 * t));
-      const float2 a2 = __ldcg(reinterpret_cast<const float2*>(qp + 16 * j + 8 + 2 * t));
+      float2 a0, a2;
+      if (fused) {   // shared memory
+        a0 = *reinterpret_cast<const float2*>(qp + 16 * j + 2 * t);
+        a2 = *reinterpret_cast<const float2*>(qp + 16 * j + 8 + 2 * t);
+      } else {
+        a0 = __ldcg(reinterpret_cast<const float2*>(qp + 16 * j + 2 * t));
+        a2 = __ldcg(reinterpret_cast<const float2*>(qp + 16 * j + 8 + 2 * t));
+      }
       qa[j][0] = pack_bf16x2(a0.x * sc, a0.y * sc);
       qa[j][1] = 0u;
       qa[j][2] = pack_bf16x2(a2.x * sc, a2.y * sc);
@@ -380,6 +423,13 @@ __global__ void __launch_bounds__(256) attn_decode_mma_kernel(const AttnDecParam
     }
     mbar_wait(&sm->bar[warp], parity);
     parity ^= 1;
+    if (appends && pg == (pos >> 6)) {   // patch the staged page with the new row (the copy may predate the store above)
+      const int r = pos & 63;
+      const int off = r * 128 + ((((2 * lane) >> 3) ^ (r & 7)) << 4) + ((2 * lane) & 7) * 2;
+      *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(sm->k[warp]) + off) = pack_bf16x2(sm->knew[2 * lane], sm->knew[2 * lane + 1]);
+      *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(sm->v[warp]) + off) = pack_bf16x2(sm->vnew[2 * lane], sm->vnew[2 * lane + 1]);
+      __syncwarp();
+    }
     float sc[8][4];
 #pragma unroll
     for (int n = 0; n < 8; ++n) {

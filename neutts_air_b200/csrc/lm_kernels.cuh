@@ -60,6 +60,13 @@ struct AttnDecParams {
   float* out;        // [B, n_heads*64]
   __nv_bfloat16* out_bf16;  // optional copy for the tensor-core o_proj
   int max_splits;
+  // Fused RoPE + KV append (tensor-core variant, batch > 4): when qkv != nullptr the kernel reads the projection output
+  // itself ([B, qkv_n] fp32, bias already added, `qkv_parts` split-K slices `qkv_pstride` floats apart, summed in slice
+  // order), rotates q / k at position seq_lens[b], appends the new K/V row to the cache and ignores `q`.
+  const float* qkv;
+  int qkv_n, qkv_parts;
+  long long qkv_pstride;
+  const float* inv_freq;
 };
 int launch_attn_decode(const AttnDecParams& p, int B, int n_layers, cudaStream_t stream);  // n_layers: extent of the KV pool
 

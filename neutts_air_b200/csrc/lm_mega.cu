@@ -241,6 +241,7 @@ __global__ void __launch_bounds__((kConsumerWarps + 1) * 32, 1) decode_mega_kern
   };
 
   AttnDecParams ap;
+  memset(&ap, 0, sizeof(ap));
   ap.q = P.q, ap.kv = P.kv, ap.n_heads = P.n_heads, ap.n_rep = n_rep, ap.scale_log2 = P.scale_log2;
   ap.part_o = P.part_o, ap.part_ml = P.part_ml, ap.counters = P.counters, ap.out = P.attn, ap.out_bf16 = nullptr;
   ap.max_splits = P.max_splits, ap.layer = 0;
