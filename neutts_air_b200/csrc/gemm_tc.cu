@@ -31,6 +31,8 @@ struct GemmEpilogue {
   int split_k;             // > 1: grid.z K-slices; slice z stores its raw partial sums at out_f32 + z * split_stride
   long long split_stride;  // (no residual / activation; bias rides on slice 0) -- the consumer adds them in z order
   int w_const;             // W is never written on the device: its first ring of tiles may load before the PDL wait
+  float* tile_max;         // optional [M][gridDim.x]: maximum of the row's stored values inside this CTA's BN columns (lm_head ->
+                           //   tile-max sampler); plain fp32 epilogue only
 };
 
 // kShallow: half-depth ring (<= 113 KB) so two CTAs share an SM -- used when the grid is between one and two
@@ -179,6 +181,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     bool row_ok = row < M;
     if (ep.valid_period > 0 && (row % ep.valid_period) >= ep.valid_len) row_ok = false;
     const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    float tmx = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t raw[32];
@@ -254,6 +257,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
       }
+      if (ep.tile_max) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || col0 + j < N) tmx = fmaxf(tmx, v[j]);
+      }
       if (ep.out_f32) {
         float* dst = ep.out_f32 + row * ep.ldc + col0;
         if (full && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -279,6 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    if (ep.tile_max && row_ok) ep.tile_max[static_cast<long long>(row) * gridDim.x + blockIdx.x] = tmx;
   }
   tc_fence_before();
   __syncthreads();
@@ -347,7 +356,17 @@ static int num_sms() {
   return n;
 }
 
-int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, bool w_const, const Split3* s3) {
+// tile width the dispatcher picks for an M x N problem (callers that consume per-tile results need to know)
+int gemm_tile_n(int M, int N, bool swiglu) {
+  const int mt = (M + 127) / 128;
+  int bn = 128;
+  if (mt * ((N + 127) / 128) < 120) bn = 64;
+  if (mt * ((N + 63) / 64) < 100) bn = 32;
+  if (swiglu && bn < 64) bn = 64;
+  return bn;
+}
+
+int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, bool w_const, const Split3* s3, float* tile_max) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return set_error(NT_ERR_INVALID, "gemm: empty problem");
   const int esz = a.dtype == NT_BF16 ? 2 : 4;
   const int bk = 128 / esz;
@@ -374,10 +393,8 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, boo
 
   // tile-N choice: keep >= ~1 wave of CTAs when the problem allows it
   const int mt = (a.M + 127) / 128;
-  int bn = 128;
-  if (mt * ((a.N + 127) / 128) < 120) bn = 64;
-  if (mt * ((a.N + 63) / 64) < 100) bn = 32;
-  if (a.act == NT_ACT_SWIGLU && bn < 64) bn = 64;
+  const int bn = gemm_tile_n(a.M, a.N, a.act == NT_ACT_SWIGLU);
+  if (tile_max && (split || a.act != NT_ACT_NONE || a.out_bf16)) return set_error(NT_ERR_INVALID, "gemm: tile maxima need the plain fp32 epilogue");
 
   if (s3 && (a.dtype != NT_TF32 || split)) return set_error(NT_ERR_INVALID, "gemm: 3xTF32 needs tf32 operands and no split-K");
   CUtensorMap ta, tb;
@@ -402,6 +419,7 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, boo
   ep.split_k = 1;
   ep.split_stride = 0;
   ep.w_const = w_const ? 1 : 0;
+  ep.tile_max = tile_max;
   if (split) {
     split->used = 1;
     const int tiles = mt * ((a.N + bn - 1) / bn);

@@ -64,8 +64,10 @@ struct SplitK {
 struct Split3 {
   int a_lo_rows, w_lo_rows;
 };
+// tile_max (optional, plain fp32 epilogue): [M][ceil(N / gemm_tile_n)] maximum of every row inside every column tile
 int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split = nullptr, bool w_const = false,
-                  const Split3* s3 = nullptr);
+                  const Split3* s3 = nullptr, float* tile_max = nullptr);
+int gemm_tile_n(int M, int N, bool swiglu);
 
 // 2-D TMA descriptor over a row-major matrix (rows x cols elements, row stride ld elements); box = box_rows x 128
 // bytes, SWIZZLE_128B (gemm_tc.cu)

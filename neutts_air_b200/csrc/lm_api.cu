@@ -377,6 +377,16 @@ static int check_sampling(const nt_lm* lm, const nt_lm_state* st, const nt_sampl
 }
 
 // lm_head on B hidden rows (fp32, un-normalised) -> lm->logits / `logits`
+// tile-max sampler after the tensor-core lm_head (batch > 4): the GEMM must tile the vocabulary by 128 columns
+static bool use_tile_sampler(const nt_lm* lm, int B) {
+  return B > gemv_max_batch() && B <= lm->tc_rows && lm->tc_tmax && gemm_tile_n(B, lm->cfg.vocab_size, false) == 128 &&
+         !env_flag("NT_NO_TILE_SAMPLER");
+}
+static int run_sampler(nt_lm* lm, const SamplerParams& s, int B, cudaStream_t stream) {
+  if (use_tile_sampler(lm, B)) return launch_sampler_tiles(s, B, lm->tc_tmax, (lm->cfg.vocab_size + 127) / 128, stream);
+  return launch_sampler(s, B, stream);
+}
+
 static int lm_head_rows(nt_lm* lm, const float* hrows, int B, float* logits, cudaStream_t stream, const SplitK* pend = nullptr) {
   const nt_lm_config& c = lm->cfg;
   if (B <= gemv_max_batch()) {
@@ -399,7 +409,7 @@ static int lm_head_rows(nt_lm* lm, const float* hrows, int B, float* logits, cud
   a.dtype = NT_BF16, a.M = B, a.N = c.vocab_size, a.K = c.hidden;
   a.A = lm->xn, a.lda = c.hidden, a.W = lm->lm_head, a.ldw = c.hidden;
   a.out_f32 = logits, a.ldc = c.vocab_size;
-  return gemm_dispatch(a, stream, nullptr, true);
+  return gemm_dispatch(a, stream, nullptr, true, nullptr, (use_tile_sampler(lm, B) && logits == lm->logits) ? lm->tc_tmax : nullptr);
 }
 
 // Transformer layers over `rows` token rows held in lm->h, via tensor-core GEMMs.
@@ -512,7 +522,7 @@ extern "C" int nt_lm_prefill(nt_lm* lm, const nt_lm_state* st, const int32_t* id
     NT_CUDA_CHECK(cudaMemcpyAsync(logits_out, lm->logits, size_t(B) * c.vocab_size * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   NT_CUDA_CHECK(cudaMemcpyAsync(st->seq_lens, lens.data(), B * sizeof(int), cudaMemcpyHostToDevice, stream));
   SamplerParams s = make_sampler(lm, st, sp);
-  if ((rc = launch_sampler(s, B, stream))) return rc;
+  if ((rc = run_sampler(lm, s, B, stream))) return rc;
   lm->prefilled = true;
   return NT_OK;
 }
@@ -565,7 +575,7 @@ static int decode_step(nt_lm* lm, const nt_lm_state* st, int B, const nt_samplin
   if ((rc = lm_head_rows(lm, lm->h, B, lm->logits, stream, &tail))) return rc;
   SamplerParams s = make_sampler(lm, st, sp);
   s.advance = 1;
-  return launch_sampler(s, B, stream);
+  return run_sampler(lm, s, B, stream);
 }
 
 extern "C" int nt_lm_decode(nt_lm* lm, const nt_lm_state* st, int B, int n_steps, const nt_sampling* sp,

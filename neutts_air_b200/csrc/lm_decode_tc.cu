@@ -986,272 +986,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
     auto sample_phase = [&] {
       const int b = blockIdx.x;
       if (b >= B) return;
-      const int nt = P.ntiles, V = P.vocab;
-      uint32_t* scratch = reinterpret_cast<uint32_t*>(uni);
-      int* tiles = reinterpret_cast<int*>(scratch + kSelScratch);   // [64] chosen tiles
-      int* counts = tiles + 64;                                      // [64] candidates per chosen tile, then offsets
-      Cand* win = reinterpret_cast<Cand*>(counts + 64);              // [2 * kTopKeep]
-      int* s_tok = reinterpret_cast<int*>(win + 2 * kTopKeep);
-      uint32_t* keys = reinterpret_cast<uint32_t*>(s_tok + 4);       // the rest of the union region
-      const int key_cap = static_cast<int>((P.uni_bytes - (kSelScratch + 128 + 4) * 4 - 2 * kTopKeep * sizeof(Cand)) / 4);
-      const float inv_t = 1.0f / P.samp.sp.temperature;
-      const bool mask_eos = ms->mask_eos[b] != 0;
-      const int eos = P.samp.sp.eos_id;
-      const bool stateless = false;
-      const int ngen = __ldcg(P.samp.n_generated + b);
-      const bool is_done = __ldcg(P.samp.done + b) != 0;
       float2* h2dst = fold_cta ? P.h2 + (static_cast<long long>(fold_no & 1) * B + b) * H : nullptr;
       const float h2stamp = __int_as_float(P.hstamp_base + fold_no);
-      const float* lg = P.logits + static_cast<long long>(b) * V;
-      pm(120);
-      // ---- direct path (large vocabularies).  Every thread takes the largest of its <= 8 tile maxima; the top_k-th
-      //      largest of those 256 values, L, is a valid candidate threshold: at least top_k distinct tiles reach it,
-      //      so the top_k logits all do (it sits a hair below the exact top_k-th tile maximum, since two of the best
-      //      tiles rarely share a thread).  Tiles whose maximum reaches L are scanned, logits >= L are ranked in
-      //      shared memory by (score desc, index asc).  Two round trips to L2, six CTA barriers, no radix passes.
-      {
-        constexpr int kPer = 8, kTileCap = 256, kCandCap = 512;
-        const int ktop = min(P.samp.sp.top_k, kTopKeep);
-        float* gmax = reinterpret_cast<float*>(keys);                         // [256]
-        int* tl = reinterpret_cast<int*>(keys + kConsumerThreads);            // [kTileCap]
-        Cand* fc = reinterpret_cast<Cand*>(keys + kConsumerThreads + kTileCap);  // [kCandCap]
-        int* cnt = ms->sel;                                                   // [0] tiles, [1] candidates, [2] L
-        if (nt <= kPer * kConsumerThreads && key_cap >= kConsumerThreads + kTileCap + 2 * kCandCap) {
-          float tm[kPer];
-          float best = -INFINITY;
-#pragma unroll
-          for (int u = 0; u < kPer; ++u) {
-            const int i = tid + u * kConsumerThreads;
-            tm[u] = (i < nt) ? __ldcg(P.tmax + static_cast<long long>(b) * nt + i) : -INFINITY;
-          }
-#pragma unroll
-          for (int u = 0; u < kPer; ++u) best = fmaxf(best, tm[u]);
-          gmax[tid] = best;
-          if (tid < 3) cnt[tid] = (tid == 2) ? __float_as_int(-INFINITY) : 0;
-          csync();
-          int rank = 0;   // (value desc, thread asc) is a total order: the ranks are a permutation of 0..255
-          for (int j4 = 0; j4 < kConsumerThreads; j4 += 4) {
-            const float4 g = *reinterpret_cast<const float4*>(gmax + j4);
-            rank += (g.x > best || (g.x == best && j4 < tid)) ? 1 : 0;
-            rank += (g.y > best || (g.y == best && j4 + 1 < tid)) ? 1 : 0;
-            rank += (g.z > best || (g.z == best && j4 + 2 < tid)) ? 1 : 0;
-            rank += (g.w > best || (g.w == best && j4 + 3 < tid)) ? 1 : 0;
-          }
-          if (rank == ktop - 1) cnt[2] = __float_as_int(best);
-          csync();
-          const float L = __int_as_float(cnt[2]);
-          pm(121);
-          if (L > -INFINITY) {   // CTA-uniform
-#pragma unroll
-            for (int u = 0; u < kPer; ++u) {
-              const bool hit = tm[u] >= L;   // padding slots hold -inf
-              const uint32_t m = __ballot_sync(0xffffffffu, hit);
-              if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&cnt[0], __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int o = base + __popc(m & ((1u << lane) - 1u));
-                if (hit && o < kTileCap) tl[o] = tid + u * kConsumerThreads;
-              }
-            }
-            csync();
-            const int ntl = cnt[0];
-            pm(122);
-            if (ntl <= kTileCap) {   // CTA-uniform
-              for (int j0 = warp; j0 < ntl; j0 += 4 * kConsumerWarps) {   // 4 tiles per warp in flight
-                float4 x[4];
-                int tile[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const int j = j0 + u * kConsumerWarps;
-                  tile[u] = (j < ntl) ? tl[j] : -1;
-                  x[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                  if (tile[u] >= 0) {
-                    const int r0 = tile[u] * 128 + lane * 4;
-                    if (r0 + 3 < V) {
-                      x[u] = __ldcg(reinterpret_cast<const float4*>(lg + r0));
-                    } else {
-                      if (r0 < V) x[u].x = __ldcg(lg + r0);
-                      if (r0 + 1 < V) x[u].y = __ldcg(lg + r0 + 1);
-                      if (r0 + 2 < V) x[u].z = __ldcg(lg + r0 + 2);
-                    }
-                  }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  if (tile[u] < 0) continue;   // warp-uniform
-                  const int r0 = tile[u] * 128 + lane * 4;
-                  const float xv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
-#pragma unroll
-                  for (int q = 0; q < 4; ++q) {
-                    const float val = (mask_eos && r0 + q == eos) ? -INFINITY : xv[q] * inv_t;   // rows >= V stayed -inf
-                    const bool hit = val >= L;
-                    const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                    if (m) {
-                      int base = 0;
-                      if (lane == 0) base = atomicAdd(&cnt[1], __popc(m));
-                      base = __shfl_sync(0xffffffffu, base, 0);
-                      const int o = base + __popc(m & ((1u << lane) - 1u));
-                      if (hit && o < kCandCap) fc[o].v = val, fc[o].i = r0 + q;
-                    }
-                  }
-                }
-              }
-              csync();
-              const int nc = cnt[1];
-              pm(123);
-              if (nc <= kCandCap) {   // CTA-uniform
-                const int k2 = min(ktop, nc);
-                for (int i = tid; i < nc; i += kConsumerThreads) {
-                  const Cand me = fc[i];
-                  int r = 0;
-                  for (int j = 0; j < nc; ++j) r += cand_before(fc[j], me) ? 1 : 0;
-                  if (r < k2) win[r] = me;
-                }
-                csync();
-                pm(124);
-                sample_finish(P.samp, b, k2, win, s_tok, stateless, ngen, is_done, csync, h2dst, h2stamp);
-                pm(125);
-                return;
-              }
-            }
-          }
-          csync();   // leave the direct path together (its scratch aliases the general path's keys)
-        }
-      }
-      for (int i = tid; i < nt; i += kConsumerThreads) keys[i] = f2key(__ldcg(P.tmax + static_cast<long long>(b) * nt + i));
-      if (tid < 64) tiles[tid] = -1, counts[tid] = 0;
-      csync();
-      const int k = min(min(P.samp.sp.top_k, kTopKeep), nt);
-      uint32_t thr;
-      int take_eq;
-      radix_select_kth(keys, nt, k, scratch, thr, take_eq, csync);
-      // fewer tiles than top_k: the tile maxima bound nothing, every logit of every tile is a candidate
-      const uint32_t cthr = nt < P.samp.sp.top_k ? 1u : thr;
-      // the k tiles: maxima above the threshold, then the first take_eq tiles (index order) that equal it
-      compact_topk(keys, nt, thr, take_eq, scratch, csync, [&](int slot, int i) { tiles[slot] = i; });
-      csync();
-      auto tile_keys = [&](int tile, uint32_t (&kk)[4]) {   // this lane's 4 logits of the tile -> processed keys
-        const int r0 = tile * 128 + lane * 4;
-        float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (r0 + 3 < V) {
-          x = __ldcg(reinterpret_cast<const float4*>(lg + r0));
-        } else {
-          if (r0 < V) x.x = __ldcg(lg + r0);
-          if (r0 + 1 < V) x.y = __ldcg(lg + r0 + 1);
-          if (r0 + 2 < V) x.z = __ldcg(lg + r0 + 2);
-        }
-        kk[0] = (r0 < V) ? processed_key(x.x, r0, mask_eos, eos, inv_t) : 0u;
-        kk[1] = (r0 + 1 < V) ? processed_key(x.y, r0 + 1, mask_eos, eos, inv_t) : 0u;
-        kk[2] = (r0 + 2 < V) ? processed_key(x.z, r0 + 2, mask_eos, eos, inv_t) : 0u;
-        kk[3] = (r0 + 3 < V) ? processed_key(x.w, r0 + 3, mask_eos, eos, inv_t) : 0u;
-      };
-      // ---- fast path: the candidates (key >= threshold) of the chosen tiles go straight into shared memory; all loads
-      //      of a warp's tiles are in flight together (one round trip to L2), the exact top-k is a rank sort.
-      constexpr int kFastCap = 512;
-      Cand* fc = reinterpret_cast<Cand*>(keys + ((nt + 3) & ~3));
-      int* fcnt = &ms->sel[1];
-      const bool fast_fits = key_cap >= ((nt + 3) & ~3) + 2 * kFastCap;
-      if (tid == 0) *fcnt = 0;
-      csync();
-      if (fast_fits) {
-        constexpr int kPerWarp = (kTopKeep + kConsumerWarps - 1) / kConsumerWarps;
-        uint32_t kk[kPerWarp][4];
-#pragma unroll
-        for (int u = 0; u < kPerWarp; ++u) {
-          const int j = warp + u * kConsumerWarps;
-          if (j < k) tile_keys(tiles[j], kk[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < kPerWarp; ++u) {
-          const int j = warp + u * kConsumerWarps;
-          if (j < k) {
-            const int tile = tiles[j];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const bool hit = kk[u][q] >= cthr && kk[u][q] != 0u;
-              const uint32_t m = __ballot_sync(0xffffffffu, hit);
-              if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(fcnt, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                const int o = base + __popc(m & ((1u << lane) - 1u));
-                if (hit && o < kFastCap) fc[o].v = key2f(kk[u][q]), fc[o].i = tile * 128 + lane * 4 + q;
-              }
-            }
-          }
-        }
-      }
-      csync();
-      const int nc = fast_fits ? *fcnt : kFastCap + 1;
-      if (nc <= kFastCap) {
-        const int k2 = min(min(P.samp.sp.top_k, kTopKeep), nc);
-        for (int i = tid; i < nc; i += kConsumerThreads) {   // rank among the candidates: (score desc, index asc) is a total order
-          const Cand me = fc[i];
-          int rank = 0;
-          for (int j = 0; j < nc; ++j) rank += cand_before(fc[j], me) ? 1 : 0;
-          if (rank < k2) win[rank] = me;
-        }
-        csync();
-        sample_finish(P.samp, b, k2, win, s_tok, stateless, ngen, is_done, csync, h2dst, h2stamp);
-        return;
-      }
-      // ---- general path (thousands of candidates: tiny vocabularies, or exact ties at the threshold)
-      // pass 1: candidates (key >= threshold) per chosen tile
-      for (int j = warp; j < k; j += kConsumerWarps) {
-        uint32_t kk[4];
-        tile_keys(tiles[j], kk);
-        int c = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) c += __popc(__ballot_sync(0xffffffffu, kk[q] >= cthr && kk[q] != 0u));
-        if (lane == 0) counts[j] = c;
-      }
-      csync();
-      if (warp == 0) {  // exclusive prefix over <= 64 tiles
-        const int c0 = counts[lane], c1 = counts[lane + 32];
-        int s0 = c0, s1 = c1;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-          const int a = __shfl_up_sync(0xffffffffu, s0, off), bb = __shfl_up_sync(0xffffffffu, s1, off);
-          if (lane >= off) s0 += a, s1 += bb;
-        }
-        const int tot0 = __shfl_sync(0xffffffffu, s0, 31);
-        const int tot = tot0 + __shfl_sync(0xffffffffu, s1, 31);
-        counts[lane] = s0 - c0;
-        counts[lane + 32] = tot0 + s1 - c1;
-        if (lane == 0) ms->sel[0] = tot;
-      }
-      csync();
-      const int ncand = min(min(ms->sel[0], key_cap), 256 * kTopKeep);   // beyond: thousands of exact ties at the threshold
-      // pass 2: write the candidates at their deterministic offsets
-      constexpr long long kCandPitch = 256 * kTopKeep;   // row pitch of the candidate arrays (sampler_scratch_floats)
-      float* cv = P.samp.cand_val + static_cast<long long>(b) * kCandPitch;
-      int32_t* ci = P.samp.cand_idx + static_cast<long long>(b) * kCandPitch;
-      for (int j = warp; j < k; j += kConsumerWarps) {
-        uint32_t kk[4];
-        const int tile = tiles[j];
-        tile_keys(tile, kk);
-        int base = counts[j];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const bool hit = kk[q] >= cthr && kk[q] != 0u;
-          const uint32_t m = __ballot_sync(0xffffffffu, hit);
-          if (hit) {
-            const int o = base + __popc(m & ((1u << lane) - 1u));
-            if (o < ncand) {
-              cv[o] = key2f(kk[q]);
-              ci[o] = tile * 128 + lane * 4 + q;
-            }
-          }
-          base += __popc(m);
-        }
-      }
-      csync();
-      sample_stage2_seq(P.samp, b, ncand, keys, scratch, win, s_tok, csync, NoMark(), kCandPitch);
-      if (h2dst) {  // the next token's embedding becomes the residual stream of the next step's first fold
-        csync();
-        for (int i = tid; i < H; i += kConsumerThreads) h2dst[i] = make_float2(P.h[static_cast<long long>(b) * H + i], h2stamp);
-      }
+      // the epilogue stored PROCESSED maxima (temperature, EOS mask): no scale, no tile to fix up
+      sample_tiles_seq(P.samp, b, P.tmax, P.ntiles, 1.0f, -1, 0.f, P.logits, P.vocab, ms->mask_eos[b] != 0, uni, P.uni_bytes, ms->sel,
+                       csync, pm, h2dst, h2stamp);
     };
 
     // =============================================================== the decode loop

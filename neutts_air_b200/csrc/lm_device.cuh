@@ -822,4 +822,288 @@ NT_DEVINL void sample_stage2_seq(const SamplerParams& p, int b, int ncand, uint3
   sample_finish(p, b, k, win, s_tok, stateless, ngen, is_done, sync);
 }
 
+// Sampler of the tile-max schemes, for sequence b, on 256 threads (0..255) of one CTA.  The lm_head epilogue left the
+// logits in HBM plus the maximum of every 128-row tile; only tiles whose maximum reaches the top_k-th best can hold a
+// top-k logit.  Direct path: every thread takes the largest of its <= 8 tile maxima; the top_k-th largest of those
+// 256 values, L, is a valid candidate threshold (at least top_k distinct tiles reach it, so the top_k logits all do);
+// tiles reaching L are scanned, logits >= L are ranked in shared memory by (score desc, index asc).  Two round trips
+// to L2, six barriers, no radix passes.  Fallbacks for small vocabularies / mass ties: radix select over the tile
+// maxima with shared-memory candidates, then the general two-pass path through the global candidate arrays.
+//   tmax: [*, nt] tile maxima (times tmax_scale = processed maxima); fix_tile >= 0: that tile's processed maximum is
+//   fix_val instead (the tile holding a masked EOS, when the maxima were taken on raw logits).
+//   uni / uni_bytes: >= 16 KB of shared scratch (1024-byte aligned); sel: >= 4 ints of shared memory.
+template <typename Sync, typename Mark>
+NT_DEVINL void sample_tiles_seq(const SamplerParams& p, int b, const float* tmax, int nt, float tmax_scale, int fix_tile, float fix_val,
+                                const float* logits, int V, bool mask_eos, uint8_t* uni, unsigned uni_bytes, int* sel, Sync sync, Mark pm,
+                                float2* h2dst, float h2stamp) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.hidden;
+  uint32_t* scratch = reinterpret_cast<uint32_t*>(uni);
+  int* tiles = reinterpret_cast<int*>(scratch + kSelScratch);   // [64] chosen tiles
+  int* counts = tiles + 64;                                      // [64] candidates per chosen tile, then offsets
+  Cand* win = reinterpret_cast<Cand*>(counts + 64);              // [2 * kTopKeep]
+  int* s_tok = reinterpret_cast<int*>(win + 2 * kTopKeep);
+  uint32_t* keys = reinterpret_cast<uint32_t*>(s_tok + 4);       // the rest of the scratch region
+  const int key_cap = static_cast<int>((uni_bytes - (kSelScratch + 128 + 4) * 4 - 2 * kTopKeep * sizeof(Cand)) / 4);
+  const float inv_t = 1.0f / p.sp.temperature;
+  const int eos = p.sp.eos_id;
+  const bool stateless = false;
+  const int ngen = __ldcg(p.n_generated + b);
+  const bool is_done = __ldcg(p.done + b) != 0;
+  const float* lg = logits + static_cast<long long>(b) * V;
+  auto tile_max = [&](int i) -> float {
+    const float v = __ldcg(tmax + static_cast<long long>(b) * nt + i) * tmax_scale;
+    return i == fix_tile ? fix_val : v;
+  };
+  pm(120);
+  // ---- direct path (large vocabularies).  Every thread takes the largest of its <= 8 tile maxima; the top_k-th
+  //      largest of those 256 values, L, is a valid candidate threshold: at least top_k distinct tiles reach it,
+  //      so the top_k logits all do (it sits a hair below the exact top_k-th tile maximum, since two of the best
+  //      tiles rarely share a thread).  Tiles whose maximum reaches L are scanned, logits >= L are ranked in
+  //      shared memory by (score desc, index asc).  Two round trips to L2, six CTA barriers, no radix passes.
+  {
+    constexpr int kPer = 8, kTileCap = 256, kCandCap = 512;
+    const int ktop = min(p.sp.top_k, kTopKeep);
+    float* gmax = reinterpret_cast<float*>(keys);                         // [256]
+    int* tl = reinterpret_cast<int*>(keys + kConsumerThreads);            // [kTileCap]
+    Cand* fc = reinterpret_cast<Cand*>(keys + kConsumerThreads + kTileCap);  // [kCandCap]
+    int* cnt = sel;                                                   // [0] tiles, [1] candidates, [2] L
+    if (nt <= kPer * kConsumerThreads && key_cap >= kConsumerThreads + kTileCap + 2 * kCandCap) {
+      float tm[kPer];
+      float best = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const int i = tid + u * kConsumerThreads;
+        tm[u] = (i < nt) ? tile_max(i) : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) best = fmaxf(best, tm[u]);
+      gmax[tid] = best;
+      if (tid < 3) cnt[tid] = (tid == 2) ? __float_as_int(-INFINITY) : 0;
+      sync();
+      int rank = 0;   // (value desc, thread asc) is a total order: the ranks are a permutation of 0..255
+      for (int j4 = 0; j4 < kConsumerThreads; j4 += 4) {
+        const float4 g = *reinterpret_cast<const float4*>(gmax + j4);
+        rank += (g.x > best || (g.x == best && j4 < tid)) ? 1 : 0;
+        rank += (g.y > best || (g.y == best && j4 + 1 < tid)) ? 1 : 0;
+        rank += (g.z > best || (g.z == best && j4 + 2 < tid)) ? 1 : 0;
+        rank += (g.w > best || (g.w == best && j4 + 3 < tid)) ? 1 : 0;
+      }
+      if (rank == ktop - 1) cnt[2] = __float_as_int(best);
+      sync();
+      const float L = __int_as_float(cnt[2]);
+      pm(121);
+      if (L > -INFINITY) {   // CTA-uniform
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+          const bool hit = tm[u] >= L;   // padding slots hold -inf
+          const uint32_t m = __ballot_sync(0xffffffffu, hit);
+          if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&cnt[0], __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int o = base + __popc(m & ((1u << lane) - 1u));
+            if (hit && o < kTileCap) tl[o] = tid + u * kConsumerThreads;
+          }
+        }
+        sync();
+        const int ntl = cnt[0];
+        pm(122);
+        if (ntl <= kTileCap) {   // CTA-uniform
+          for (int j0 = warp; j0 < ntl; j0 += 4 * kConsumerWarps) {   // 4 tiles per warp in flight
+            float4 x[4];
+            int tile[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int j = j0 + u * kConsumerWarps;
+              tile[u] = (j < ntl) ? tl[j] : -1;
+              x[u] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+              if (tile[u] >= 0) {
+                const int r0 = tile[u] * 128 + lane * 4;
+                if (r0 + 3 < V) {
+                  x[u] = __ldcg(reinterpret_cast<const float4*>(lg + r0));
+                } else {
+                  if (r0 < V) x[u].x = __ldcg(lg + r0);
+                  if (r0 + 1 < V) x[u].y = __ldcg(lg + r0 + 1);
+                  if (r0 + 2 < V) x[u].z = __ldcg(lg + r0 + 2);
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (tile[u] < 0) continue;   // warp-uniform
+              const int r0 = tile[u] * 128 + lane * 4;
+              const float xv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float val = (mask_eos && r0 + q == eos) ? -INFINITY : xv[q] * inv_t;   // rows >= V stayed -inf
+                const bool hit = val >= L;
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (m) {
+                  int base = 0;
+                  if (lane == 0) base = atomicAdd(&cnt[1], __popc(m));
+                  base = __shfl_sync(0xffffffffu, base, 0);
+                  const int o = base + __popc(m & ((1u << lane) - 1u));
+                  if (hit && o < kCandCap) fc[o].v = val, fc[o].i = r0 + q;
+                }
+              }
+            }
+          }
+          sync();
+          const int nc = cnt[1];
+          pm(123);
+          if (nc <= kCandCap) {   // CTA-uniform
+            const int k2 = min(ktop, nc);
+            for (int i = tid; i < nc; i += kConsumerThreads) {
+              const Cand me = fc[i];
+              int r = 0;
+              for (int j = 0; j < nc; ++j) r += cand_before(fc[j], me) ? 1 : 0;
+              if (r < k2) win[r] = me;
+            }
+            sync();
+            pm(124);
+            sample_finish(p, b, k2, win, s_tok, stateless, ngen, is_done, sync, h2dst, h2stamp);
+            pm(125);
+            return;
+          }
+        }
+      }
+      sync();   // leave the direct path together (its scratch aliases the general path's keys)
+    }
+  }
+  for (int i = tid; i < nt; i += kConsumerThreads) keys[i] = f2key(tile_max(i));
+  if (tid < 64) tiles[tid] = -1, counts[tid] = 0;
+  sync();
+  const int k = min(min(p.sp.top_k, kTopKeep), nt);
+  uint32_t thr;
+  int take_eq;
+  radix_select_kth(keys, nt, k, scratch, thr, take_eq, sync);
+  // fewer tiles than top_k: the tile maxima bound nothing, every logit of every tile is a candidate
+  const uint32_t cthr = nt < p.sp.top_k ? 1u : thr;
+  // the k tiles: maxima above the threshold, then the first take_eq tiles (index order) that equal it
+  compact_topk(keys, nt, thr, take_eq, scratch, sync, [&](int slot, int i) { tiles[slot] = i; });
+  sync();
+  auto tile_keys = [&](int tile, uint32_t (&kk)[4]) {   // this lane's 4 logits of the tile -> processed keys
+    const int r0 = tile * 128 + lane * 4;
+    float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    if (r0 + 3 < V) {
+      x = __ldcg(reinterpret_cast<const float4*>(lg + r0));
+    } else {
+      if (r0 < V) x.x = __ldcg(lg + r0);
+      if (r0 + 1 < V) x.y = __ldcg(lg + r0 + 1);
+      if (r0 + 2 < V) x.z = __ldcg(lg + r0 + 2);
+    }
+    kk[0] = (r0 < V) ? processed_key(x.x, r0, mask_eos, eos, inv_t) : 0u;
+    kk[1] = (r0 + 1 < V) ? processed_key(x.y, r0 + 1, mask_eos, eos, inv_t) : 0u;
+    kk[2] = (r0 + 2 < V) ? processed_key(x.z, r0 + 2, mask_eos, eos, inv_t) : 0u;
+    kk[3] = (r0 + 3 < V) ? processed_key(x.w, r0 + 3, mask_eos, eos, inv_t) : 0u;
+  };
+  // ---- fast path: the candidates (key >= threshold) of the chosen tiles go straight into shared memory; all loads
+  //      of a warp's tiles are in flight together (one round trip to L2), the exact top-k is a rank sort.
+  constexpr int kFastCap = 512;
+  Cand* fc = reinterpret_cast<Cand*>(keys + ((nt + 3) & ~3));
+  int* fcnt = &sel[1];
+  const bool fast_fits = key_cap >= ((nt + 3) & ~3) + 2 * kFastCap;
+  if (tid == 0) *fcnt = 0;
+  sync();
+  if (fast_fits) {
+    constexpr int kPerWarp = (kTopKeep + kConsumerWarps - 1) / kConsumerWarps;
+    uint32_t kk[kPerWarp][4];
+#pragma unroll
+    for (int u = 0; u < kPerWarp; ++u) {
+      const int j = warp + u * kConsumerWarps;
+      if (j < k) tile_keys(tiles[j], kk[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kPerWarp; ++u) {
+      const int j = warp + u * kConsumerWarps;
+      if (j < k) {
+        const int tile = tiles[j];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const bool hit = kk[u][q] >= cthr && kk[u][q] != 0u;
+          const uint32_t m = __ballot_sync(0xffffffffu, hit);
+          if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(fcnt, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const int o = base + __popc(m & ((1u << lane) - 1u));
+            if (hit && o < kFastCap) fc[o].v = key2f(kk[u][q]), fc[o].i = tile * 128 + lane * 4 + q;
+          }
+        }
+      }
+    }
+  }
+  sync();
+  const int nc = fast_fits ? *fcnt : kFastCap + 1;
+  if (nc <= kFastCap) {
+    const int k2 = min(min(p.sp.top_k, kTopKeep), nc);
+    for (int i = tid; i < nc; i += kConsumerThreads) {   // rank among the candidates: (score desc, index asc) is a total order
+      const Cand me = fc[i];
+      int rank = 0;
+      for (int j = 0; j < nc; ++j) rank += cand_before(fc[j], me) ? 1 : 0;
+      if (rank < k2) win[rank] = me;
+    }
+    sync();
+    sample_finish(p, b, k2, win, s_tok, stateless, ngen, is_done, sync, h2dst, h2stamp);
+    return;
+  }
+  // ---- general path (thousands of candidates: tiny vocabularies, or exact ties at the threshold)
+  // pass 1: candidates (key >= threshold) per chosen tile
+  for (int j = warp; j < k; j += kConsumerWarps) {
+    uint32_t kk[4];
+    tile_keys(tiles[j], kk);
+    int c = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c += __popc(__ballot_sync(0xffffffffu, kk[q] >= cthr && kk[q] != 0u));
+    if (lane == 0) counts[j] = c;
+  }
+  sync();
+  if (warp == 0) {  // exclusive prefix over <= 64 tiles
+    const int c0 = counts[lane], c1 = counts[lane + 32];
+    int s0 = c0, s1 = c1;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, s0, off), bb = __shfl_up_sync(0xffffffffu, s1, off);
+      if (lane >= off) s0 += a, s1 += bb;
+    }
+    const int tot0 = __shfl_sync(0xffffffffu, s0, 31);
+    const int tot = tot0 + __shfl_sync(0xffffffffu, s1, 31);
+    counts[lane] = s0 - c0;
+    counts[lane + 32] = tot0 + s1 - c1;
+    if (lane == 0) sel[0] = tot;
+  }
+  sync();
+  const int ncand = min(min(sel[0], key_cap), 256 * kTopKeep);   // beyond: thousands of exact ties at the threshold
+  // pass 2: write the candidates at their deterministic offsets
+  constexpr long long kCandPitch = 256 * kTopKeep;   // row pitch of the candidate arrays (sampler_scratch_floats)
+  float* cv = p.cand_val + static_cast<long long>(b) * kCandPitch;
+  int32_t* ci = p.cand_idx + static_cast<long long>(b) * kCandPitch;
+  for (int j = warp; j < k; j += kConsumerWarps) {
+    uint32_t kk[4];
+    const int tile = tiles[j];
+    tile_keys(tile, kk);
+    int base = counts[j];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const bool hit = kk[q] >= cthr && kk[q] != 0u;
+      const uint32_t m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int o = base + __popc(m & ((1u << lane) - 1u));
+        if (o < ncand) {
+          cv[o] = key2f(kk[q]);
+          ci[o] = tile * 128 + lane * 4 + q;
+        }
+      }
+      base += __popc(m);
+    }
+  }
+  sync();
+  sample_stage2_seq(p, b, ncand, keys, scratch, win, s_tok, sync, NoMark(), kCandPitch);
+  if (h2dst) {  // the next token's embedding becomes the residual stream of the next step's first fold
+    sync();
+    for (int i = tid; i < H; i += kConsumerThreads) h2dst[i] = make_float2(p.h[static_cast<long long>(b) * H + i], h2stamp);
+  }
+}
+
 }  // namespace nt

@@ -579,6 +579,56 @@ int launch_sampler(const SamplerParams& p, int B, cudaStream_t stream) {
   return launch_kernel(topk_stage2_kernel, dim3(B), dim3(kConsumerThreads), smem, stream, true, p, ncand);
 }
 
+// Tile-max sampler for the tensor-core lm_head GEMM (batch > 4): the GEMM epilogue left the RAW maximum of every
+// 128-column tile per sequence; one CTA per sequence picks the candidate tiles from those maxima and ranks the few
+// dozen candidate logits (sample_tiles_seq, the scheme of the persistent decode kernel).  Replaces topk_stage1 (a
+// radix select over every 2048-logit chunk: 98 us at batch 64) + topk_stage2 (29 us) by one ~20 us launch.
+struct NoMarkI {
+  NT_DEVINL void operator()(int) const {}
+};
+constexpr unsigned kTilesScratch = 96 * 1024;
+__global__ void __launch_bounds__(kConsumerThreads) topk_tiles_kernel(const SamplerParams p, const float* tmax, const int nt) {
+  extern __shared__ uint8_t tiles_raw[];
+  uint8_t* uni = tiles_raw + ((1024u - (smem_u32(tiles_raw) & 1023u)) & 1023u);
+  __shared__ int sel[8];
+  __shared__ float fix;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool mask_eos = __ldcg(p.n_generated + b) < p.sp.min_new_tokens;
+  const float inv_t = 1.0f / p.sp.temperature;
+  int fix_tile = -1;
+  float fix_val = 0.f;
+  if (mask_eos) {   // the raw maximum of the tile that holds EOS may be the (masked) EOS logit itself: redo that tile without it
+    fix_tile = p.sp.eos_id >> 7;
+    if (warp == 0) {
+      float m = -INFINITY;
+      for (int q = 0; q < 4; ++q) {
+        const int r = fix_tile * 128 + lane * 4 + q;
+        if (r < p.V && r != p.sp.eos_id) m = fmaxf(m, __ldcg(p.logits + static_cast<long long>(b) * p.V + r));
+      }
+      m = warp_max(m);
+      if (lane == 0) fix = m * inv_t;
+    }
+    __syncthreads();
+    fix_val = fix;
+  }
+  sample_tiles_seq(p, b, tmax, nt, inv_t, fix_tile, fix_val, p.logits, p.V, mask_eos, uni, kTilesScratch, sel, SyncAll(), NoMarkI(),
+                   static_cast<float2*>(nullptr), 0.f);
+}
+
+int launch_sampler_tiles(const SamplerParams& p, int B, const float* tmax, int nt, cudaStream_t stream) {
+  if (int rc0 = launch_sampler_check(p)) return rc0;
+  if (p.n_generated_override) return set_error(NT_ERR_INVALID, "tile-max sampler: stateless mode unsupported");
+  static bool attr = false;
+  const int smem = int(kTilesScratch) + 1024;
+  if (!attr) {
+    NT_CUDA_CHECK(cudaFuncSetAttribute(topk_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr = true;
+  }
+  return launch_kernel(topk_tiles_kernel, dim3(B), dim3(kConsumerThreads), smem, stream, true, p, tmax, nt);
+}
+
 // =================================================================================== prefill helpers
 __global__ void embed_rows_kernel(const __nv_bfloat16* embed, const int32_t* ids, int hidden, float* h) {
   pdl_launch_dependents();

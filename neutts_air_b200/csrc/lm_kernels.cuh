@@ -100,6 +100,8 @@ struct SamplerParams {
 };
 int launch_sampler(const SamplerParams& p, int B, cudaStream_t stream);
 int launch_sampler_check(const SamplerParams& p);
+// tmax: [B][nt] RAW maxima of the 128-column tiles of p.logits (GEMM epilogue, gemm_dispatch(..., tile_max))
+int launch_sampler_tiles(const SamplerParams& p, int B, const float* tmax, int nt, cudaStream_t stream);
 size_t sampler_scratch_floats(int B, int V);  // per-array element count for cand_val / cand_idx
 int sampler_nchunks(int V);
 

@@ -63,16 +63,19 @@ def test_full_size_batch_invariance_and_reproducibility(full_lm):
     assert [o.tolist() for o in outs[0]] == [o.tolist() for o in outs[1]]
 
 
-@pytest.mark.parametrize("B", [1, 3, 6])
-def test_decode_kernel_sampler_matches_standalone_sampler(full_lm, B):
+@pytest.mark.parametrize("B,impl", [(1, None), (3, None), (6, None), (6, "perop")],
+                         ids=["persistent-b1", "persistent-b3", "persistent-b6", "chain-b6-tile-sampler"])
+def test_decode_kernel_sampler_matches_standalone_sampler(full_lm, B, impl, monkeypatch):
     """The persistent decode kernel samples inside the kernel (tile maxima -> candidate tiles -> exact top-k ->
-    Philox draw).  Given the logits it returns for a step, the stand-alone sampler op (``nt_op_topk_sample``, pinned
+    Philox draw); the per-op chain runs the same scheme as a kernel of its own behind the lm_head GEMM.  Given the logits it returns for a step, the stand-alone sampler op (``nt_op_topk_sample``, pinned
     to the HF processors + multinomial by tests/test_gpu_kernels.py) must pick the very same token: same top-50 set,
     same probabilities, same Philox counter (seed, slot, n_generated).  Covers the EOS mask (min_new_tokens) too."""
     import ctypes as C
 
     from neutts_air_b200 import _lib
 
+    if impl:   # the per-op chain: tensor-core lm_head with tile maxima in its epilogue + topk_tiles_kernel
+        monkeypatch.setenv("NT_DECODE_IMPL", impl)
     lm, eos, n_steps = full_lm, 151670, 9
     L = _lib.lib()
     prompts = [_prompt(40 + 17 * i, 30 + i) for i in range(B)]
