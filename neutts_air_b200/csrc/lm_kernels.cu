@@ -695,9 +695,51 @@ __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(float* x, const float
     }
   }
 }
+// Few rows (batched decode): one CTA per row, one float4 per thread, the residual + every split-K slice + the norm
+// weight loaded in ONE round trip (the warp-per-row kernel above walks the slices one dependent round trip at a time:
+// 6 us per launch at 5 slices, 49 launches per decode step).  Slices are added in slice order, the sum of squares is
+// reduced in a fixed order: bit-reproducible.  cols <= 1024, nparts <= 8.
+__global__ void __launch_bounds__(256) rmsnorm_rows_wide_kernel(float* x, const float* w, float eps, int cols, float* out_f32,
+                                                                __nv_bfloat16* out_bf16, const float* parts, int nparts,
+                                                                long long pstride) {
+  __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x, i = threadIdx.x, nvec = cols >> 2;
+  float4* xr = reinterpret_cast<float4*>(x + static_cast<long long>(row) * cols);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f), g = v;
+  if (i < nvec) {
+    v = xr[i];
+    g = __ldg(reinterpret_cast<const float4*>(w) + i);
+    float4 t[8];
+#pragma unroll
+    for (int z = 0; z < 8; ++z)
+      if (z < nparts) t[z] = __ldcg(reinterpret_cast<const float4*>(parts + z * pstride + static_cast<long long>(row) * cols) + i);
+#pragma unroll
+    for (int z = 0; z < 8; ++z)
+      if (z < nparts) v.x += t[z].x, v.y += t[z].y, v.z += t[z].z, v.w += t[z].w;
+    if (nparts > 0) xr[i] = v;
+  }
+  const float ss = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+  if ((i & 31) == 0) red[i >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += red[k];
+  const float sc = rsqrtf(tot / static_cast<float>(cols) + eps);
+  if (i < nvec) {
+    const float4 o = make_float4(g.x * (v.x * sc), g.y * (v.y * sc), g.z * (v.z * sc), g.w * (v.w * sc));
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + static_cast<long long>(row) * cols)[i] = o;
+    if (out_bf16) reinterpret_cast<uint2*>(out_bf16 + static_cast<long long>(row) * cols)[i] = make_uint2(pack_bf16x2(o.x, o.y), pack_bf16x2(o.z, o.w));
+  }
+}
+
 int launch_rmsnorm_rows(const float* x, const float* w, float eps, int rows, int cols, float* out_f32,
                         __nv_bfloat16* out_bf16, cudaStream_t s, const float* parts, int nparts, long long pstride) {
   if (cols % 4) return set_error(NT_ERR_INVALID, "rmsnorm: cols must be a multiple of 4");
+  if (rows <= 256 && cols <= 1024 && nparts <= 8)
+    return launch_kernel(rmsnorm_rows_wide_kernel, dim3(rows), dim3(256), 0, s, true, const_cast<float*>(x), w, eps, cols, out_f32,
+                         out_bf16, parts, nparts, pstride);
   // few rows (batched decode): one warp per CTA so the rows spread over the SMs; many rows (prefill): 8 per CTA
   const int wpc = rows >= 2048 ? 8 : (rows >= 512 ? 2 : 1);
   return launch_kernel(rmsnorm_rows_kernel, dim3((rows + wpc - 1) / wpc), dim3(32 * wpc), 0, s, true, const_cast<float*>(x), w, eps,
