@@ -393,7 +393,11 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, boo
 
   // tile-N choice: keep >= ~1 wave of CTAs when the problem allows it
   const int mt = (a.M + 127) / 128;
-  const int bn = gemm_tile_n(a.M, a.N, a.act == NT_ACT_SWIGLU);
+  int bn = gemm_tile_n(a.M, a.N, a.act == NT_ACT_SWIGLU);
+  if (a.act == NT_ACT_SWIGLU && mt == 1) {   // experiments: tile width of the batched-decode gate/up GEMM
+    static const int force = [] { const char* e = getenv("NT_GEMM_GU_BN"); return e ? atoi(e) : 0; }();
+    if (force == 64 || force == 128) bn = force;
+  }
   if (tile_max && (split || a.act != NT_ACT_NONE || a.out_bf16)) return set_error(NT_ERR_INVALID, "gemm: tile maxima need the plain fp32 epilogue");
 
   if (s3 && (a.dtype != NT_TF32 || split)) return set_error(NT_ERR_INVALID, "gemm: 3xTF32 needs tf32 operands and no split-K");
