@@ -335,12 +335,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmE
                        int kb_per_tap, cudaStream_t stream, int a_lo_rows = 0, int w_lo_rows = 0) {
   const int splits = ep.split_k > 1 ? ep.split_k : 1;
   using Cfg = GemmCfg<BN, kShallow, kS3>;
-  static bool attr_set = false;
-  auto kern = gemm_tc_kernel<kFmt, BN, kShallow, kS3>;
-  if (!attr_set) {
-    NT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_set = true;
-  }
+  auto kern = gemm_tc_kernel<kFmt, BN, kShallow, kS3>;   // launch_kernel opts in to the dynamic shared memory per device
   dim3 grid((N + BN - 1) / BN, (M + Cfg::BM - 1) / Cfg::BM, splits);
   return launch_kernel(kern, grid, dim3(256), Cfg::SMEM_BYTES, stream, /*pdl=*/true, ta, tb, ep, M, N, num_kb,
                        kb_per_tap, a_lo_rows, w_lo_rows);

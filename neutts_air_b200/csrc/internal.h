@@ -18,6 +18,8 @@ bool pdl_disabled();  // NT_NO_PDL=1: launch without the programmatic-dependent-
 // Every kernel of the library asks for the maximum shared-memory carveout, so consecutive kernels never force the
 // SM to switch its L1 / shared-memory split (the big-tile kernels need ~180 KB; the small ones do not use L1 much).
 void prefer_max_smem_carveout(const void* kernel);
+// opt-in to > 48 KB of dynamic shared memory, once per (kernel, device)
+int ensure_dynamic_smem(const void* kernel, size_t bytes);
 
 #define NT_CUDA_CHECK(expr)                                                                          \
   do {                                                                                               \
@@ -32,6 +34,7 @@ template <typename... KArgs, typename... Args>
 int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
                   Args&&... args) {
   prefer_max_smem_carveout(reinterpret_cast<const void*>(kernel));
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), smem)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;

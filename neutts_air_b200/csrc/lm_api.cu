@@ -44,16 +44,41 @@ static int mega_max_batch() {
   const int n = e ? atoi(e) : 4;
   return n < 1 ? 1 : (n > 16 ? 16 : n);
 }
+// Function attributes are per device context: a process that runs engines on two GPUs (backbone on cuda:0, codec on
+// cuda:1) must set them on both.  One table keyed by (kernel, device ordinal) serves the carve-out preference and the
+// dynamic shared-memory limit of every launch that goes through launch_kernel().
+struct KernelAttrState {
+  bool carveout = false;
+  size_t dyn_smem = 0;
+};
+static KernelAttrState& kernel_attr_state(const void* kernel, std::unique_lock<std::mutex>& lock) {
+  static std::mutex mu;
+  static std::vector<std::pair<std::pair<const void*, int>, KernelAttrState>> table;
+  lock = std::unique_lock<std::mutex>(mu);
+  int dev = 0;
+  cudaGetDevice(&dev);
+  for (auto& e : table)
+    if (e.first.first == kernel && e.first.second == dev) return e.second;
+  table.push_back({{kernel, dev}, KernelAttrState()});
+  return table.back().second;
+}
 void prefer_max_smem_carveout(const void* kernel) {
   static const bool off = env_flag("NT_NO_CARVEOUT");
-  if (off) return;
-  static std::mutex mu;
-  static std::vector<const void*> seen;
-  std::lock_guard<std::mutex> lock(mu);
-  for (const void* k : seen)
-    if (k == kernel) return;
-  seen.push_back(kernel);
-  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  std::unique_lock<std::mutex> lock;
+  KernelAttrState& st = kernel_attr_state(kernel, lock);
+  if (st.carveout) return;
+  st.carveout = true;
+  if (!off) cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+int ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  if (bytes <= 48 * 1024) return NT_OK;
+  std::unique_lock<std::mutex> lock;
+  KernelAttrState& st = kernel_attr_state(kernel, lock);
+  if (st.dyn_smem >= bytes) return NT_OK;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+  if (e != cudaSuccess) return set_error(NT_ERR_CUDA, "cudaFuncSetAttribute(%zu B of dynamic shared memory) failed: %s", bytes, cudaGetErrorString(e));
+  st.dyn_smem = bytes;
+  return NT_OK;
 }
 bool pdl_disabled() {
   static const bool off = env_flag("NT_NO_PDL");

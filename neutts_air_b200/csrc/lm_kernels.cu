@@ -148,17 +148,12 @@ int launch_gemv(const GemvParams& p, int nb, int num_sms, cudaStream_t stream) {
   GemvSmemPlan plan = gemv_plan(p.K, nb);
   if (plan.total > 227 * 1024) return set_error(NT_ERR_INVALID, "gemv: K=%d needs %zu B of shared memory", p.K, plan.total);
   const int grid = min(num_sms, p.rows / 2);
-  static size_t attr_bytes[5] = {0, 0, 0, 0, 0};
   void (*kern)(const GemvParams, const GemvSmemPlan) = nullptr;
   switch (nb) {
     case 1: kern = gemv_kernel<1>; break;
     case 2: kern = gemv_kernel<2>; break;
     case 3: kern = gemv_kernel<3>; break;
     default: kern = gemv_kernel<4>; break;
-  }
-  if (attr_bytes[nb] < plan.total) {
-    NT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(plan.total)));
-    attr_bytes[nb] = plan.total;
   }
   return launch_kernel(kern, dim3(grid), dim3(kGemvThreads), plan.total, stream, true, p, plan);
 }
@@ -510,21 +505,11 @@ __global__ void __launch_bounds__(256) attn_decode_mma_kernel(const AttnDecParam
 
 int launch_attn_decode(const AttnDecParams& p, int B, int n_layers, cudaStream_t stream) {
   if (p.n_rep < 1 || p.n_rep > 8) return set_error(NT_ERR_INVALID, "attention: %d query heads per KV head unsupported (1..8)", p.n_rep);
-  static bool attr_set = false;
   const int smem = int(sizeof(AttnWarpSmem)) + 1024;
-  if (!attr_set) {
-    NT_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
-  }
   CUtensorMap kmap;
   if (int rc = kv_pool_tmap(p.kv, n_layers, &kmap)) return rc;
   if (B > 4) {  // tensor-core variant: bf16 query / probabilities, like every other GEMM input of the batched path
-    static bool mma_attr = false;
     const int msmem = int(sizeof(AttnMmaSmem)) + 1024;
-    if (!mma_attr) {
-      NT_CUDA_CHECK(cudaFuncSetAttribute(attn_decode_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, msmem));
-      mma_attr = true;
-    }
     return launch_kernel(attn_decode_mma_kernel, dim3(p.kv.n_kv_heads, B), dim3(256), msmem, stream, true, p, kmap);
   }
   return launch_kernel(attn_decode_kernel, dim3(p.kv.n_kv_heads, B), dim3(32 * kAttnWarps), smem, stream, true, p, kmap);
@@ -571,11 +556,6 @@ int launch_sampler(const SamplerParams& p, int B, cudaStream_t stream) {
   const size_t smem = size_t(ncand) * sizeof(uint32_t);
   int rc = launch_kernel(topk_stage1_kernel, dim3(p.nchunks, B), dim3(kConsumerThreads), 0, stream, true, p);
   if (rc) return rc;
-  static size_t attr = 0;
-  if (smem > 40 * 1024 && attr < smem) {
-    NT_CUDA_CHECK(cudaFuncSetAttribute(topk_stage2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr = smem;
-  }
   return launch_kernel(topk_stage2_kernel, dim3(B), dim3(kConsumerThreads), smem, stream, true, p, ncand);
 }
 
@@ -620,12 +600,7 @@ __global__ void __launch_bounds__(kConsumerThreads) topk_tiles_kernel(const Samp
 int launch_sampler_tiles(const SamplerParams& p, int B, const float* tmax, int nt, cudaStream_t stream) {
   if (int rc0 = launch_sampler_check(p)) return rc0;
   if (p.n_generated_override) return set_error(NT_ERR_INVALID, "tile-max sampler: stateless mode unsupported");
-  static bool attr = false;
   const int smem = int(kTilesScratch) + 1024;
-  if (!attr) {
-    NT_CUDA_CHECK(cudaFuncSetAttribute(topk_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr = true;
-  }
   return launch_kernel(topk_tiles_kernel, dim3(B), dim3(kConsumerThreads), smem, stream, true, p, tmax, nt);
 }
 

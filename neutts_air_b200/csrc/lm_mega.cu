@@ -431,11 +431,7 @@ int launch_decode_mega(MegaParams& P, int nb, int num_sms, cudaStream_t stream) 
     case 3: kern = decode_mega_kernel<3>; break;
     default: kern = decode_mega_kernel<4>; break;
   }
-  static size_t attr[5] = {0, 0, 0, 0, 0};
-  if (attr[nb] < smem) {
-    NT_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    attr[nb] = smem;
-  }
+  if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), smem)) return rc;   // per (kernel, device)
   int per_sm = 0;
   NT_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (kConsumerWarps + 1) * 32, smem));
   if (per_sm < 1) return set_error(NT_ERR_CUDA, "megakernel: a CTA does not fit on an SM (%zu B shared memory)", smem);
