@@ -232,7 +232,7 @@ _WEIGHTS = {}
 SPEECH_BASE, EOS = 151936, 151670
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE decode_tc_kernel launch (249 steps, batch 1, contexts 500..749)
 # from profiles/decode_tc_b1_r2_ncu_summary.txt (ncu --set full); None until a capture of the current kernel exists
-NCU_TRAFFIC_B1 = 278.65e9
+NCU_TRAFFIC_B1 = 278.50e9
 
 
 def build_engines(device, batch, prefill_tokens=None):

@@ -878,9 +878,11 @@ NT_DEVINL void sample_tiles_seq(const SamplerParams& p, int b, const float* tmax
       }
 #pragma unroll
       for (int u = 0; u < kPer; ++u) best = fmaxf(best, tm[u]);
+      pm(126);
       gmax[tid] = best;
       if (tid < 3) cnt[tid] = (tid == 2) ? __float_as_int(-INFINITY) : 0;
       sync();
+      pm(127);
       int rank = 0;   // (value desc, thread asc) is a total order: the ranks are a permutation of 0..255
       for (int j4 = 0; j4 < kConsumerThreads; j4 += 4) {
         const float4 g = *reinterpret_cast<const float4*>(gmax + j4);
@@ -889,6 +891,7 @@ NT_DEVINL void sample_tiles_seq(const SamplerParams& p, int b, const float* tmax
         rank += (g.z > best || (g.z == best && j4 + 2 < tid)) ? 1 : 0;
         rank += (g.w > best || (g.w == best && j4 + 3 < tid)) ? 1 : 0;
       }
+      pm(128);
       if (rank == ktop - 1) cnt[2] = __float_as_int(best);
       sync();
       const float L = __int_as_float(cnt[2]);

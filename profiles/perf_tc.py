@@ -49,7 +49,7 @@ if timeline and impl == "tc":
     names = {0: "step start", 1: "fold: start", 2: "fold: polled", 4: "fold: staged", 5: "fold: bop ready", 10: "epilogue: accumulator ready",
              21: "attn: page issued", 22: "attn: qkv polled", 23: "attn: page landed", 25: "attn: stored", 31: "merge: polled+staged",
              32: "merge: bop ready", 41: "act: polled+staged", 42: "act: bop ready", 50: "swiglu: accumulator ready",
-             105: "PHASE fold(o) done", 106: "PHASE fold(down) done", 120: "sampler: start", 121: "sampler: threshold", 122: "sampler: tiles listed", 123: "sampler: candidates gathered", 124: "sampler: ranked", 125: "sampler: finished", 110: "PHASE lm_head done", 111: "PHASE sampler done", 100: "PHASE qkv done", 101: "PHASE attention done", 102: "PHASE o_proj done", 103: "PHASE gate/up done", 104: "PHASE down done",
+             105: "PHASE fold(o) done", 106: "PHASE fold(down) done", 120: "sampler: start", 126: "sampler: maxima loaded", 127: "sampler: maxima shared", 128: "sampler: ranked maxima", 121: "sampler: threshold", 122: "sampler: tiles listed", 123: "sampler: candidates gathered", 124: "sampler: ranked", 125: "sampler: finished", 110: "PHASE lm_head done", 111: "PHASE sampler done", 100: "PHASE qkv done", 101: "PHASE attention done", 102: "PHASE o_proj done", 103: "PHASE gate/up done", 104: "PHASE down done",
              200: "grid barrier released"}
     for cta in (0, 1):
         raw = buf[cta * 1024: cta * 1024 + 1024].cpu().tolist()
@@ -84,6 +84,6 @@ if timeline and impl == "tc":
             if j < len(fine):
                 print(f"    +{(fine[j][0] - t0) / 1e3:7.2f}  {names.get(fine[j][1], fine[j][1])}")
 
-        samp = [(tt, i) for tt, i in zip(ts, ids) if 120 <= i <= 125 or i == 111]
+        samp = [(tt, i) for tt, i in zip(ts, ids) if 120 <= i <= 128 or i == 111]
         if samp:
             print("  sampler (us since start): " + ", ".join(f"{names.get(i, i)} +{(tt - samp[0][0]) / 1e3:.2f}" for tt, i in samp))
