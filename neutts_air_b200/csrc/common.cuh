@@ -111,6 +111,21 @@ NT_DEVINL void tma_load_2d(void* smem_dst, const CUtensorMap* m, int c0, int c1,
       : "memory");
 }
 
+// Same with an L2 eviction-priority hint (createpolicy): weights that stream through once per decode step are loaded
+// evict_first so that they do not push the small hot set (KV pages, hand-off buffers, logits) out of the 126 MB L2.
+NT_DEVINL uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+NT_DEVINL void tma_load_2d_hint(void* smem_dst, const CUtensorMap* m, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 NT_DEVINL void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 NT_DEVINL void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -31,6 +31,7 @@ struct GemmEpilogue {
   int split_k;             // > 1: grid.z K-slices; slice z stores its raw partial sums at out_f32 + z * split_stride
   long long split_stride;  // (no residual / activation; bias rides on slice 0) -- the consumer adds them in z order
   int w_const;             // W is never written on the device: its first ring of tiles may load before the PDL wait
+  int w_stream;            // W is read exactly once by this launch (one row tile): fetch it with the L2 evict_first policy
   float* tile_max;         // optional [M][gridDim.x]: maximum of the row's stored values inside this CTA's BN columns (lm_head ->
                            //   tile-max sampler); plain fp32 epilogue only
 };
@@ -102,12 +103,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // kernel ever writes -- while the previous kernel is still finishing.
   pdl_launch_dependents();
   const int early = ep.w_const ? min(STAGES, kb_hi - kb_lo) : 0;
+  const uint64_t wpol = ep.w_stream ? l2_policy_evict_first() : 0ull;
+  auto load_w = [&](void* dst, int c0, int c1, uint64_t* bar) {
+    if (wpol) tma_load_2d_hint(dst, &tmB, c0, c1, bar, wpol);
+    else tma_load_2d(dst, &tmB, c0, c1, bar);
+  };
   if (warp == 0) {
     if (elect_one()) {
       for (int i = 0; i < early; ++i) {
         mbar_arrive_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
-        tma_load_2d(tiles + i * Cfg::STAGE_BYTES + W_OFF, &tmB, (kb_lo + i) * BK_ELEMS, n0, &full_bar[i]);
-        if (kS3) tma_load_2d(tiles + i * Cfg::STAGE_BYTES + W_OFF + Cfg::B_BYTES, &tmB, (kb_lo + i) * BK_ELEMS, n0 + w_lo_rows, &full_bar[i]);
+        load_w(tiles + i * Cfg::STAGE_BYTES + W_OFF, (kb_lo + i) * BK_ELEMS, n0, &full_bar[i]);
+        if (kS3) load_w(tiles + i * Cfg::STAGE_BYTES + W_OFF + Cfg::B_BYTES, (kb_lo + i) * BK_ELEMS, n0 + w_lo_rows, &full_bar[i]);
       }
     }
   }
@@ -131,8 +137,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tma_load_2d(sa, &tmA, acol, m0 + tap, &full_bar[s]);
         if (kS3) tma_load_2d(sa + Cfg::A_BYTES, &tmA, acol, m0 + tap + a_lo_rows, &full_bar[s]);
         if (!b_in_flight) {
-          tma_load_2d(sb, &tmB, kb * BK_ELEMS, n0, &full_bar[s]);
-          if (kS3) tma_load_2d(sb + Cfg::B_BYTES, &tmB, kb * BK_ELEMS, n0 + w_lo_rows, &full_bar[s]);
+          load_w(sb, kb * BK_ELEMS, n0, &full_bar[s]);
+          if (kS3) load_w(sb + Cfg::B_BYTES, kb * BK_ELEMS, n0 + w_lo_rows, &full_bar[s]);
         }
       }
     }
@@ -419,6 +425,7 @@ int gemm_dispatch(const nt_gemm_args& a, cudaStream_t stream, SplitK* split, boo
   ep.split_stride = 0;
   ep.w_const = w_const ? 1 : 0;
   ep.tile_max = tile_max;
+  ep.w_stream = (w_const && mt == 1 && !getenv("NT_GEMM_NO_EVICT_FIRST")) ? 1 : 0;
   if (split) {
     split->used = 1;
     const int tiles = mt * ((a.N + bn - 1) / bn);

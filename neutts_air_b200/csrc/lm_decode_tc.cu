@@ -245,6 +245,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
     // re-executed at every use: it is also the point where the lanes RECONVERGE after a data-dependent wait loop --
     // the compiler emits the TMA / MMA instruction itself unpredicated (only its operand moves are predicated), so a
     // lane group that reached it without the leader would issue it with stale operands.
+    // weights pass through L2 once per step: evict_first keeps KV pages, hand-off buffers and logits resident
+    const uint64_t wpolicy = P.weights_evict_first ? l2_policy_evict_first() : 0ull;
     int slot = 0;
     uint32_t par = 0;       // parity of the slot's NEXT completion of empty_bar that we must have seen
     bool wrapped = false;   // ring used at least once
@@ -252,7 +254,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) decode_tc_kernel(const __grid_c
       if (wrapped) mbar_wait(&ms->empty_bar[slot], par ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&ms->full_bar[slot], 16384);
-        tma_load_2d(ring + static_cast<size_t>(slot) * 16384, m, kcol, row, &ms->full_bar[slot]);
+        if (wpolicy) tma_load_2d_hint(ring + static_cast<size_t>(slot) * 16384, m, kcol, row, &ms->full_bar[slot], wpolicy);
+        else tma_load_2d(ring + static_cast<size_t>(slot) * 16384, m, kcol, row, &ms->full_bar[slot]);
       }
       if (++slot == NS) slot = 0, par ^= 1, wrapped = true;
     };
@@ -1303,6 +1306,7 @@ int launch_decode_tc(TcParams& P, int B, int num_sms, const TcPlanInfo& info, cu
   const int nt = B <= 16 ? 16 : (B <= 32 ? 32 : 64);
   if (info.max_chunks > 14) return set_error(NT_ERR_INVALID, "decode_tc: %d k-blocks per CTA exceed the staging area", info.max_chunks);
   P.fold_in_cta = tc_fold_in_cta(B, P.hidden) ? 1 : 0;
+  P.weights_evict_first = getenv("NT_TC_NO_EVICT_FIRST") ? 0 : 1;
   if (info.gu_split && !P.fold_in_cta) return set_error(NT_ERR_INVALID, "decode_tc: the flat plan needs the in-CTA fold (batch <= 4)");
   const bool hilo = B <= 8;
   if (hilo) return P.fold_in_cta ? launch_tc<16, true, true>(P, num_sms, stream) : launch_tc<16, true, false>(P, num_sms, stream);

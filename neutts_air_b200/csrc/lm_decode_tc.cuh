@@ -83,6 +83,7 @@ struct TcParams {
   int att_warps;                  // page-walking warps of the attention phase (2 | 4)
   unsigned att_off;               // attention staging: inside the union region (aliased) or behind it (batch <= 4: pages prefetched)
   int fold_in_cta;                // 1: batch <= 4, consumers fold the split-K slices themselves (no fold phases)
+  int weights_evict_first;        // 1: weight tiles are fetched with the L2 evict_first policy
 };
 
 struct TcShape {  // everything the planner needs
