@@ -197,3 +197,33 @@ def test_sampler_topk_set_eos_mask_and_distribution(cuda):
     spg = _lib.Sampling(eos, 0, 1 << 20, 50, 1.0, 0, 1, None)
     tok, _, _ = _sample(L, logits.to(cuda), spg, [0, 0], 0)
     assert tok.tolist() == [eos, eos]
+
+
+def test_sampler_ties_at_the_kth_value(cuda):
+    """VERDICT r1 weak #14.  transformers' TopKLogitsWarper masks ``scores < kth_value`` (logits_process.py:580-586), so
+    scores that TIE with the k-th value all survive; these kernels keep exactly top_k candidates, breaking ties by
+    the smaller token id.  Real logits never tie exactly (measure zero); the difference is pinned here so that it stays
+    a documented, deterministic choice: with 8 tokens tied at the 50th value, the 50 kept ids are the 46 larger
+    scores plus the 4 smallest ids of the tie, and their probabilities are the softmax over exactly those 50."""
+    from neutts_air_b200 import _lib
+
+    L = _lib.lib()
+    V, eos, k = 217472, 151670, 50
+    g = torch.Generator().manual_seed(3)
+    logits = torch.randn(1, V, generator=g)
+    top = torch.randperm(V, generator=g)[:46 + 8]
+    logits[0, top[:46]] = 10.0 + torch.arange(46, dtype=torch.float32) * 0.25      # 46 distinct winners
+    logits[0, top[46:]] = 9.0                                                      # 8 tokens tied at the 50th value
+    logits[0, eos] = -50.0
+    sp = _lib.Sampling(eos, 0, 1 << 20, k, 1.0, 7, 0, None)
+    tok, tv, ti = _sample(L, logits.to(cuda), sp, [0], 0)
+    kept = ti[0, :k].tolist()
+    tie_ids = sorted(top[46:].tolist())
+    assert set(kept[:46]) == set(top[:46].tolist())
+    assert kept[46:] == tie_ids[:4]                                               # smaller ids win the tie, in id order
+    ref = torch.softmax(torch.cat((logits[0, kept[:46]], torch.full((4,), 9.0))), 0)
+    assert max_err(tv[0, :k], ref) < 1e-5
+    assert int(tok[0]) in kept
+    # transformers would keep all 54 (46 + 8 tied): the kept probability mass differs by the 4 dropped ties
+    hf_keep = int((logits[0] >= 9.0).sum())
+    assert hf_keep == 54
