@@ -27,6 +27,16 @@ def _worker(rank, world, port, q):
         wavs = [np.full(480 * lens[i], float(i), dtype=np.float32) for i in mine]     # ragged lengths
         allw = dist.all_gather_waveforms(wavs, mine, len(lens), device="cpu", lengths=lens)
         ok = all(len(allw[i]) == 480 * lens[i] and float(allw[i][0]) == float(i) and float(allw[i][-1]) == float(i) for i in range(5))
+        # bounded job (bench.py, fixed-length utterances): t_max known -> the all-gather is the ONLY collective; tensors
+        # (as a device engine returns them) are accepted as well as numpy arrays; over-long waveforms are refused
+        wt = [torch.full((480 * lens[i],), float(i)) for i in mine]
+        allt = dist.all_gather_waveforms(wt, mine, len(lens), device="cpu", t_max=480 * 50)
+        ok = ok and all(len(allt[i]) == 480 * lens[i] and float(allt[i][-1]) == float(i) for i in range(5))
+        try:
+            dist.all_gather_waveforms(wt, mine, len(lens), device="cpu", t_max=100)
+            ok = False
+        except ValueError:
+            pass
 
         # facade path: every rank ends up with every waveform
         import warnings
