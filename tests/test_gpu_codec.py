@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import codec_oracle as CO
-from tests.helpers import make_codec, max_err, rel_err
+from tests.helpers import make_codec, max_err
 
 pytestmark = pytest.mark.gpu
 
