@@ -534,7 +534,7 @@ def main_b200(args):
         "metric": "audio-sec/sec (RTF), NeuTTS-Air 500 prefill / 250 decode + NeuCodec decode",
         "value": total_audio / t_dev, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
-        "dtype": "bf16 weights+KV / f32 accumulate (LM), tf32 tensor cores (codec)", "data": "synthetic",
+        "dtype": "bf16 weights+KV / f32 accumulate (LM), 3xTF32 = fp32-grade tensor-core GEMMs (codec)", "data": "synthetic",
         "config": {"workload": (f"configs[2]: mixed-length prompts U{{200..1400}} (mean {sum(lens) / len(lens):.0f}) / 250 decode tokens + NeuCodec "
                                 f"decode to 24 kHz, batch={B} per GPU" if mixed else
                                 (f"configs[3]: global batch {B * world} sharded {B} utterances/GPU over {world} GPUs, 500 prefill / 250 decode tokens + "
